@@ -1,0 +1,137 @@
+"""tnc_b200 -- B200-native pairwise tensor-contraction hot path of qc-tum/TNC.
+
+Host-side mirror (Python, over the C ABI in include/tncb.h) of the reference's interface for
+this path: `tensornetwork.tensor.Tensor`, `tensornetwork.tensordata.TensorData`,
+`contractionpath.ContractionPath`, `tensornetwork.contraction.contract_tensor_network`,
+`builders.circuit_builder.Circuit` / `Permutor`, and `dist.communication` for the
+partitioned fan-in (tnc::mpi::communication).  All numerics run in libtncb200 (CUDA, sm_100a);
+nothing here computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import numpy as np
+
+from ._lib import TncbError, check, lib, u64_array
+
+__all__ = ["Context", "DeviceTensor", "TncbError", "contract_pair", "default_context", "lib"]
+
+
+class Context:
+    """One device + stream + arena (tncb_ctx)."""
+
+    def __init__(self, device: int = 0, arena_bytes: int = 0):
+        self._l = lib()
+        h = C.c_void_p()
+        check(self._l.tncb_ctx_create(device, arena_bytes, C.byref(h)))
+        self.handle = h
+        self.device = device
+
+    def synchronize(self) -> None:
+        check(self._l.tncb_ctx_synchronize(self.handle))
+
+    @property
+    def stream(self) -> int:
+        return int(self._l.tncb_ctx_stream(self.handle) or 0)
+
+    def stats(self) -> dict:
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        check(self._l.tncb_ctx_stats(self.handle, C.byref(a), C.byref(b), C.byref(c)))
+        return {"kernel_launches": a.value, "arena_peak_bytes": b.value, "arena_live_bytes": c.value}
+
+    def reset_stats(self) -> None:
+        check(self._l.tncb_ctx_reset_stats(self.handle))
+
+    def close(self) -> None:
+        if getattr(self, "handle", None):
+            self._l.tncb_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+class DeviceTensor:
+    """A device-resident complex128 tensor (tncb_tensor), row-major."""
+
+    def __init__(self, ctx: Context, handle, shape: Sequence[int]):
+        self.ctx = ctx
+        self.handle = handle
+        self.shape = tuple(int(s) for s in shape)
+
+    @classmethod
+    def from_numpy(cls, ctx: Context, arr: np.ndarray) -> "DeviceTensor":
+        a = np.ascontiguousarray(arr, dtype=np.complex128)
+        h = C.c_void_p()
+        check(ctx._l.tncb_tensor_upload(ctx.handle, a.ndim, u64_array(a.shape), a.ctypes.data_as(C.c_void_p), C.byref(h)))
+        return cls(ctx, h, a.shape)
+
+    @classmethod
+    def empty(cls, ctx: Context, shape: Sequence[int]) -> "DeviceTensor":
+        h = C.c_void_p()
+        check(ctx._l.tncb_tensor_alloc(ctx.handle, len(shape), u64_array(shape), C.byref(h)))
+        return cls(ctx, h, shape)
+
+    @classmethod
+    def adopt(cls, ctx: Context, handle) -> "DeviceTensor":
+        l = ctx._l
+        r = l.tncb_tensor_rank(handle)
+        dims = u64_array([0] * max(r, 1))
+        check(l.tncb_tensor_dims(handle, dims))
+        return cls(ctx, handle, [dims[i] for i in range(r)])
+
+    def to_numpy(self) -> np.ndarray:
+        if self.handle is None:
+            raise TncbError(-3, "Cannot convert uncontracted tensor to data")
+        out = np.empty(self.shape, dtype=np.complex128)
+        check(self.ctx._l.tncb_tensor_download(self.ctx.handle, self.handle, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def device_ptr(self) -> int:
+        return int(self.ctx._l.tncb_tensor_device_ptr(self.handle) or 0)
+
+    def release(self):
+        """Give up ownership (the C side consumed the handle)."""
+        h, self.handle = self.handle, None
+        return h
+
+    def free(self) -> None:
+        if self.handle is not None and self.ctx.handle is not None:
+            self.ctx._l.tncb_tensor_free(self.ctx.handle, self.handle)
+        self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def contract_pair(ctx: Context, a_legs, a, b_legs, b):
+    """tetra::contract equivalent for host arrays: returns (out_legs, ndarray).
+    out legs = (b \\ a) ++ (a \\ b) (contraction.rs:64, tensor.rs:463-479)."""
+    da = a if isinstance(a, DeviceTensor) else DeviceTensor.from_numpy(ctx, np.asarray(a))
+    db = b if isinstance(b, DeviceTensor) else DeviceTensor.from_numpy(ctx, np.asarray(b))
+    out_legs = [l for l in b_legs if l not in a_legs] + [l for l in a_legs if l not in b_legs]
+    h = C.c_void_p()
+    check(ctx._l.tncb_contract_pair(ctx.handle, len(out_legs), u64_array(out_legs),
+                                    len(a_legs), u64_array(a_legs), da.handle,
+                                    len(b_legs), u64_array(b_legs), db.handle, C.byref(h)))
+    da.release(); db.release()
+    out = DeviceTensor.adopt(ctx, h)
+    return out_legs, out.to_numpy()

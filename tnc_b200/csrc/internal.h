@@ -1,0 +1,106 @@
+// Internal definitions shared by the host runtime and the CUDA kernels of libtncb200.
+#pragma once
+#include <cstdint>
+#include <cstddef>
+#include <string>
+#include <vector>
+#include <map>
+#include <cuda_runtime.h>
+#include "../../include/tncb.h"
+
+namespace tncb {
+
+constexpr int kMaxLegs = 64;   // max rank of a tensor accepted at the ABI
+constexpr int kMaxGroups = 40; // max fused leg groups per list passed to a kernel
+
+// A list of (fused) legs of one index class, outermost first, innermost last.
+struct LegList {
+  int n;
+  int _pad;
+  long long dim[kMaxGroups];
+  long long sa[kMaxGroups]; // element stride in operand A (or in the only operand)
+  long long sb[kMaxGroups]; // element stride in operand B (K-list only)
+};
+
+// The GEMM view of one pairwise contraction  C[N,M] = sum_K Bt[N,K] * At[K,M]
+// (SURVEY 3.4): M = legs(a)\legs(b) in a's order, N = legs(b)\legs(a) in b's
+// order, K = shared legs.  C is plain row-major [N][M], which *is* the
+// reference's output layout (b\a)++(a\b) (tensor.rs:463-479).
+struct PairPlan {
+  std::vector<uint64_t> out_legs, out_dims;
+  long long M = 1, N = 1, K = 1;
+  LegList m{}, n{}, k{};  // m: strides in A; n: strides in B (stored in .sa); k: sa=A, sb=B
+  int kernel_class = 0;   // 0 = K0, 1 = K1
+  // K1 loader modes: true = consecutive threads walk the K index, false = the free index
+  bool a_kfast = false, b_kfast = true;
+  double flops() const { return 8.0 * (double)M * (double)N * (double)K; }
+  double bytes() const { return 16.0 * ((double)M * K + (double)K * N + (double)M * N); }
+};
+
+// Returns TNCB_OK or an error; fills plan. Pure host code (no CUDA calls).
+int plan_pair(int n_a, const uint64_t* a_legs, const uint64_t* a_dims,
+              int n_b, const uint64_t* b_legs, const uint64_t* b_dims, PairPlan& plan);
+
+void set_error(const std::string& msg);
+int fail(int status, const std::string& msg);
+
+// ---- device arena -------------------------------------------------------------------
+struct Slab { char* base; size_t size; std::map<size_t, size_t> free_by_off; };
+
+struct Arena {
+  std::vector<Slab> slabs;
+  size_t capacity_limit = 0; // 0 = device free memory
+  size_t reserved = 0, live = 0, peak = 0;
+  size_t next_slab = (size_t)256 << 20;
+  int alloc(size_t bytes, void** out);
+  void free(void* p, size_t bytes);
+  void release_all();
+};
+
+} // namespace tncb
+
+struct tncb_tensor {
+  double2* ptr = nullptr;
+  int rank = 0;
+  uint64_t dims[tncb::kMaxLegs];
+  uint64_t elems = 1;
+  size_t bytes = 0;      // arena bytes (0 = not owned by the arena)
+  bool owned = true;
+};
+
+struct NcclApi;
+
+struct tncb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  tncb::Arena arena;
+  uint64_t launches = 0;
+  int sm_count = 148;
+  // pinned staging for leaf uploads
+  void* stage_host = nullptr; size_t stage_bytes = 0;
+  // K1 offset-table workspace (grown on demand, stream-ordered reuse)
+  long long* tab = nullptr; size_t tab_elems = 0;
+  // split-K partial workspace
+  double2* partial = nullptr; size_t partial_elems = 0;
+  // NCCL
+  void* nccl_comm = nullptr; int world = 1, rank = 0;
+};
+
+namespace tncb {
+// ---- kernel launchers (kernels.cu) ---------------------------------------------------
+int launch_pair(tncb_ctx* ctx, const PairPlan& p, const double2* A, const double2* B, double2* C);
+int launch_permute(tncb_ctx* ctx, const double2* in, double2* out, int rank,
+                   const uint64_t* in_dims, const int* perm);
+int launch_conj(tncb_ctx* ctx, double2* data, uint64_t elems);
+int ensure_tab(tncb_ctx* ctx, size_t elems);
+int ensure_partial(tncb_ctx* ctx, size_t elems);
+
+int tensor_new(tncb_ctx* ctx, int rank, const uint64_t* dims, tncb_tensor** out);
+} // namespace tncb
+
+#define TNCB_CUDA(call)                                                                   \
+  do {                                                                                    \
+    cudaError_t _e = (call);                                                              \
+    if (_e != cudaSuccess)                                                                \
+      return tncb::fail(TNCB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e)); \
+  } while (0)

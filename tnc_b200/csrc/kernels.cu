@@ -1,0 +1,474 @@
+// sm_100a kernels of the pairwise-contraction hot path (replaces tetra::contract, called at
+// tnc/src/tensornetwork/contraction.rs:78-84, i.e. HPTT transposes + faer/MKL ZGEMM).
+//
+//   C[n, m] = sum_k Bt[n, k] * At[k, m]      (complex128, C row-major [N][M])
+//   Bt[n, k] = B[offBn(n) + offBk(k)],  At[k, m] = A[offAm(m) + offAk(k)]
+//
+// The permutes of the reference's TTGT are never materialised: both operands are gathered
+// through separable mixed-radix offset functions while the tile is staged into shared memory.
+//
+//   K0  strided kernel: G lanes per output element cooperate over K (shuffle reduction),
+//       optional deterministic split-K; for tiny and for low-intensity pairs.
+//   K1  fused gather + ZGEMM: cp.async 16-byte gathers into a fragment-ordered shared-memory
+//       ring, FP64 tensor-core DMMA (mma.sync.m8n8k4.f64, 4 real MMAs per complex tile).
+//       tcgen05.mma has no f64 kind, so the FP64 tensor path on sm_100a is DMMA; measured
+//       peak 37.2 TFLOP/s (profiles/r01_fp64_peak_microbench.txt).
+#include "internal.h"
+#include <algorithm>
+#include <cstdio>
+
+namespace tncb {
+
+// ------------------------------------------------------------------------------------------
+// index helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long decomp_a(long long idx, const LegList& L) {
+  long long off = 0;
+  for (int g = L.n - 1; g > 0; --g) {
+    long long d = L.dim[g];
+    long long q = idx / d;
+    off += (idx - q * d) * L.sa[g];
+    idx = q;
+  }
+  if (L.n > 0) off += idx * L.sa[0];
+  return off;
+}
+
+__device__ __forceinline__ void decomp_ab(long long idx, const LegList& L, long long& oa, long long& ob) {
+  long long a = 0, b = 0;
+  for (int g = L.n - 1; g > 0; --g) {
+    long long d = L.dim[g];
+    long long q = idx / d;
+    long long r = idx - q * d;
+    a += r * L.sa[g];
+    b += r * L.sb[g];
+    idx = q;
+  }
+  if (L.n > 0) { a += idx * L.sa[0]; b += idx * L.sb[0]; }
+  oa = a; ob = b;
+}
+
+// ------------------------------------------------------------------------------------------
+// K0: strided kernel with G cooperating lanes per output and optional split-K
+// ------------------------------------------------------------------------------------------
+struct K0Args {
+  LegList m, n, k;
+  long long M, N, K;
+  long long kchunk; // K range handled by one blockIdx.y
+};
+
+constexpr int K0_THREADS = 256;
+constexpr int K0_KT = 1024;
+
+template <int G>
+__global__ void __launch_bounds__(K0_THREADS)
+k0_kernel(const double2* __restrict__ A, const double2* __restrict__ B, double2* __restrict__ dst,
+          const __grid_constant__ K0Args p) {
+  __shared__ long long s_ka[K0_KT];
+  __shared__ long long s_kb[K0_KT];
+  const int tid = threadIdx.x;
+  const int lane_g = tid % G;
+  const long long MN = p.M * p.N;
+  const long long o = (long long)blockIdx.x * (K0_THREADS / G) + tid / G;
+  const bool valid = o < MN;
+  long long n = 0, m = 0;
+  if (valid) { n = o / p.M; m = o - n * p.M; }
+  const long long offA0 = decomp_a(m, p.m);
+  const long long offB0 = decomp_a(n, p.n);
+  const long long kbeg = (long long)blockIdx.y * p.kchunk;
+  const long long kend = min(p.K, kbeg + p.kchunk);
+  double cr = 0.0, ci = 0.0;
+  for (long long kb = kbeg; kb < kend; kb += K0_KT) {
+    const int cnt = (int)min((long long)K0_KT, kend - kb);
+    __syncthreads();
+    for (int i = tid; i < cnt; i += K0_THREADS) {
+      long long oa, ob;
+      decomp_ab(kb + i, p.k, oa, ob);
+      s_ka[i] = oa; s_kb[i] = ob;
+    }
+    __syncthreads();
+    if (valid) {
+#pragma unroll 4
+      for (int i = lane_g; i < cnt; i += G) {
+        const double2 a = __ldg(A + offA0 + s_ka[i]);
+        const double2 b = __ldg(B + offB0 + s_kb[i]);
+        cr = fma(b.x, a.x, cr); cr = fma(-b.y, a.y, cr);
+        ci = fma(b.x, a.y, ci); ci = fma(b.y, a.x, ci);
+      }
+    }
+  }
+#pragma unroll
+  for (int d = G / 2; d > 0; d >>= 1) {
+    cr += __shfl_xor_sync(0xffffffffu, cr, d);
+    ci += __shfl_xor_sync(0xffffffffu, ci, d);
+  }
+  if (valid && lane_g == 0) dst[(long long)blockIdx.y * MN + o] = make_double2(cr, ci);
+}
+
+__global__ void reduce_partials_kernel(const double2* __restrict__ part, double2* __restrict__ C,
+                                       long long MN, int ksplit) {
+  long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= MN) return;
+  double cr = 0.0, ci = 0.0;
+  for (int s = 0; s < ksplit; s++) { double2 v = part[(long long)s * MN + o]; cr += v.x; ci += v.y; }
+  C[o] = make_double2(cr, ci);
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: fused gather + DMMA ZGEMM
+// ------------------------------------------------------------------------------------------
+__global__ void build_tables_kernel(const __grid_constant__ LegList m, const __grid_constant__ LegList n,
+                                    const __grid_constant__ LegList k, long long M, long long N, long long K,
+                                    long long* __restrict__ tab) {
+  const long long total = M + N + 2 * K;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    if (i < M) tab[i] = decomp_a(i, m);
+    else if (i < M + N) tab[i] = decomp_a(i - M, n);
+    else if (i < M + N + K) { long long oa, ob; decomp_ab(i - M - N, k, oa, ob); tab[i] = oa; tab[i + K] = ob; }
+  }
+}
+
+__device__ __forceinline__ void cp_async16(unsigned smem_addr, const void* gptr, bool pred) {
+  const int src = pred ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_addr), "l"(gptr), "r"(src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N_>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N_)); }
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
+}
+
+constexpr int K1_BK = 16;
+
+struct K1Args {
+  const double2* A;
+  const double2* B;
+  double2* C;
+  const long long* offAm;
+  const long long* offBn;
+  const long long* offAk;
+  const long long* offBk;
+  long long M, N, K;
+  int tiles_m, tiles_n;
+};
+
+// Shared-memory tiles are stored in DMMA fragment order so that every fragment load is one
+// conflict-free 512-byte LDS.128 per warp:
+//   row operand Bt (rows n, cols k):  slot = ((n/8)*(BK/4) + k/4)*32 + (n%8)*4 + k%4
+//   col operand At (rows k, cols m):  slot = ((k/4)*(BM/8) + m/8)*32 + (m%8)*4 + k%4
+template <int BN, int BM, int WARPS_N, int WARPS_M, int STAGES, bool B_KFAST, bool A_KFAST>
+__global__ void __launch_bounds__(WARPS_N* WARPS_M * 32)
+k1_kernel(const __grid_constant__ K1Args p) {
+  constexpr int BK = K1_BK;
+  constexpr int NT = WARPS_N * WARPS_M * 32;
+  constexpr int TI = BN / WARPS_N / 8; // 8-row blocks per warp
+  constexpr int TJ = BM / WARPS_M / 8; // 8-col blocks per warp
+  constexpr int B_EPT = BN * BK / NT;
+  constexpr int A_EPT = BK * BM / NT;
+  constexpr int STAGE_ELEMS = BN * BK + BK * BM;
+  static_assert(BN * BK % NT == 0 && BK * BM % NT == 0, "tile/threads mismatch");
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2* smem = reinterpret_cast<double2*>(smem_raw);
+  const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem);
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int wn = warp / WARPS_M;
+  const int wm = warp % WARPS_M;
+
+  // grouped rasterisation: 8 n-tiles share the same band of At columns in L2
+  int tn, tm;
+  {
+    const int GROUP = 8;
+    const int t = blockIdx.x;
+    const int per_group = GROUP * p.tiles_m;
+    const int gid = t / per_group;
+    const int first_n = gid * GROUP;
+    const int gsize = min(p.tiles_n - first_n, GROUP);
+    const int r = t - gid * per_group;
+    tn = first_n + r % gsize;
+    tm = r / gsize;
+  }
+  const long long n0 = (long long)tn * BN;
+  const long long m0 = (long long)tm * BM;
+
+  // per-thread gather rows/cols (constant over the K loop)
+  long long b_off[B_EPT]; int b_slot[B_EPT]; int b_kk[B_EPT]; bool b_ok[B_EPT];
+#pragma unroll
+  for (int j = 0; j < B_EPT; j++) {
+    const int e = tid + j * NT;
+    const int kk = B_KFAST ? (e % BK) : (e / BN);
+    const int row = B_KFAST ? (e / BK) : (e % BN);
+    const long long gn = n0 + row;
+    b_ok[j] = gn < p.N;
+    b_off[j] = __ldg(p.offBn + (b_ok[j] ? gn : 0));
+    b_kk[j] = kk;
+    b_slot[j] = ((row >> 3) * (BK / 4) + (kk >> 2)) * 32 + (row & 7) * 4 + (kk & 3);
+  }
+  long long a_off[A_EPT]; int a_slot[A_EPT]; int a_kk[A_EPT]; bool a_ok[A_EPT];
+#pragma unroll
+  for (int j = 0; j < A_EPT; j++) {
+    const int e = tid + j * NT;
+    const int kk = A_KFAST ? (e % BK) : (e / BM);
+    const int col = A_KFAST ? (e / BK) : (e % BM);
+    const long long gm = m0 + col;
+    a_ok[j] = gm < p.M;
+    a_off[j] = __ldg(p.offAm + (a_ok[j] ? gm : 0));
+    a_kk[j] = kk;
+    a_slot[j] = BN * BK + ((kk >> 2) * (BM / 8) + (col >> 3)) * 32 + (col & 7) * 4 + (kk & 3);
+  }
+
+  auto load_stage = [&](int stage, long long k0) {
+    const unsigned sbase = smem_base + (unsigned)(stage * STAGE_ELEMS) * 16u;
+#pragma unroll
+    for (int j = 0; j < B_EPT; j++) {
+      const long long gk = k0 + b_kk[j];
+      const bool ok = b_ok[j] && gk < p.K;
+      const long long ko = __ldg(p.offBk + (gk < p.K ? gk : 0));
+      cp_async16(sbase + (unsigned)b_slot[j] * 16u, p.B + (b_off[j] + ko), ok);
+    }
+#pragma unroll
+    for (int j = 0; j < A_EPT; j++) {
+      const long long gk = k0 + a_kk[j];
+      const bool ok = a_ok[j] && gk < p.K;
+      const long long ko = __ldg(p.offAk + (gk < p.K ? gk : 0));
+      cp_async16(sbase + (unsigned)a_slot[j] * 16u, p.A + (a_off[j] + ko), ok);
+    }
+  };
+
+  double cr[TI][TJ][2], ci[TI][TJ][2];
+#pragma unroll
+  for (int i = 0; i < TI; i++)
+#pragma unroll
+    for (int j = 0; j < TJ; j++) { cr[i][j][0] = cr[i][j][1] = 0.0; ci[i][j][0] = ci[i][j][1] = 0.0; }
+
+  const int nk = (int)((p.K + BK - 1) / BK);
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; s++) {
+    if (s < nk) load_stage(s, (long long)s * BK);
+    cp_async_commit();
+  }
+
+  for (int kc = 0; kc < nk; kc++) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {
+      const int nxt = kc + STAGES - 1;
+      if (nxt < nk) load_stage(nxt % STAGES, (long long)nxt * BK);
+      cp_async_commit();
+    }
+    const double2* sB = smem + (kc % STAGES) * STAGE_ELEMS;
+    const double2* sA = sB + BN * BK;
+#pragma unroll
+    for (int kb = 0; kb < BK / 4; kb++) {
+      double2 bf[TI], af[TJ];
+#pragma unroll
+      for (int i = 0; i < TI; i++) bf[i] = sB[((wn * TI + i) * (BK / 4) + kb) * 32 + lane];
+#pragma unroll
+      for (int j = 0; j < TJ; j++) af[j] = sA[(kb * (BM / 8) + wm * TJ + j) * 32 + lane];
+#pragma unroll
+      for (int i = 0; i < TI; i++) {
+        const double nbi = -bf[i].y;
+#pragma unroll
+        for (int j = 0; j < TJ; j++) {
+          dmma884(cr[i][j][0], cr[i][j][1], bf[i].x, af[j].x);
+          dmma884(ci[i][j][0], ci[i][j][1], bf[i].x, af[j].y);
+          dmma884(cr[i][j][0], cr[i][j][1], nbi, af[j].y);
+          dmma884(ci[i][j][0], ci[i][j][1], bf[i].y, af[j].x);
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+
+  // epilogue: D fragment (row = lane/4, cols = 2*(lane%4) + {0,1}) -> C row-major [N][M]
+  const int g = lane >> 2, t2 = (lane & 3) * 2;
+#pragma unroll
+  for (int i = 0; i < TI; i++) {
+    const long long gn = n0 + (wn * TI + i) * 8 + g;
+    if (gn >= p.N) continue;
+#pragma unroll
+    for (int j = 0; j < TJ; j++) {
+      const long long gm = m0 + (wm * TJ + j) * 8 + t2;
+      double2* dst = p.C + gn * p.M + gm;
+      if (gm < p.M) dst[0] = make_double2(cr[i][j][0], ci[i][j][0]);
+      if (gm + 1 < p.M) dst[1] = make_double2(cr[i][j][1], ci[i][j][1]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// permute (Permutor::apply / tetra transpose) and conjugate
+// ------------------------------------------------------------------------------------------
+__global__ void permute_kernel(const double2* __restrict__ in, double2* __restrict__ out,
+                               const __grid_constant__ LegList L, long long total) {
+  for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total;
+       o += (long long)gridDim.x * blockDim.x)
+    out[o] = __ldg(in + decomp_a(o, L));
+}
+
+__global__ void conj_kernel(double2* __restrict__ d, long long total) {
+  for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total;
+       o += (long long)gridDim.x * blockDim.x)
+    d[o].y = -d[o].y;
+}
+
+// ------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------
+int ensure_tab(tncb_ctx* ctx, size_t elems) {
+  if (ctx->tab_elems >= elems) return TNCB_OK;
+  // stream-ordered: earlier kernels still reading the old table finish before the free
+  if (ctx->tab) TNCB_CUDA(cudaFreeAsync(ctx->tab, ctx->stream));
+  size_t want = std::max(elems, (size_t)1 << 20);
+  TNCB_CUDA(cudaMallocAsync((void**)&ctx->tab, want * sizeof(long long), ctx->stream));
+  ctx->tab_elems = want;
+  return TNCB_OK;
+}
+
+int ensure_partial(tncb_ctx* ctx, size_t elems) {
+  if (ctx->partial_elems >= elems) return TNCB_OK;
+  if (ctx->partial) TNCB_CUDA(cudaFreeAsync(ctx->partial, ctx->stream));
+  size_t want = std::max(elems, (size_t)1 << 18);
+  TNCB_CUDA(cudaMallocAsync((void**)&ctx->partial, want * sizeof(double2), ctx->stream));
+  ctx->partial_elems = want;
+  return TNCB_OK;
+}
+
+template <int G>
+static void launch_k0_g(dim3 grid, cudaStream_t st, const double2* A, const double2* B, double2* dst, const K0Args& a) {
+  k0_kernel<G><<<grid, K0_THREADS, 0, st>>>(A, B, dst, a);
+}
+
+static int launch_k0(tncb_ctx* ctx, const PairPlan& P, const double2* A, const double2* B, double2* C) {
+  K0Args a;
+  a.m = P.m; a.n = P.n; a.k = P.k; a.M = P.M; a.N = P.N; a.K = P.K;
+  const long long MN = P.M * P.N;
+  const long long target = (long long)ctx->sm_count * 1024; // lanes wanted in flight
+  int G = 1;
+  while (G < 32 && MN * G < target && (long long)G * 2 <= P.K) G *= 2;
+  long long ksplit = 1;
+  const long long per_lane = P.K / G;
+  if (MN * G < target && per_lane > 64) {
+    ksplit = std::min(target / std::max(1LL, MN * G), per_lane / 32);
+    ksplit = std::max(1LL, std::min(ksplit, 1024LL));
+  }
+  a.kchunk = (P.K + ksplit - 1) / ksplit;
+  ksplit = (P.K + a.kchunk - 1) / a.kchunk;
+  double2* dst = C;
+  if (ksplit > 1) {
+    int rc = ensure_partial(ctx, (size_t)(MN * ksplit));
+    if (rc) return rc;
+    dst = ctx->partial;
+  }
+  const long long per_block = K0_THREADS / G;
+  const long long blocks = (MN + per_block - 1) / per_block;
+  if (blocks > 0x7fffffffLL) return fail(TNCB_ERR_UNSUPPORTED, "K0 grid too large");
+  dim3 grid((unsigned)blocks, (unsigned)ksplit);
+  switch (G) {
+    case 1: launch_k0_g<1>(grid, ctx->stream, A, B, dst, a); break;
+    case 2: launch_k0_g<2>(grid, ctx->stream, A, B, dst, a); break;
+    case 4: launch_k0_g<4>(grid, ctx->stream, A, B, dst, a); break;
+    case 8: launch_k0_g<8>(grid, ctx->stream, A, B, dst, a); break;
+    case 16: launch_k0_g<16>(grid, ctx->stream, A, B, dst, a); break;
+    default: launch_k0_g<32>(grid, ctx->stream, A, B, dst, a); break;
+  }
+  ctx->launches++;
+  if (ksplit > 1) {
+    reduce_partials_kernel<<<(unsigned)((MN + 255) / 256), 256, 0, ctx->stream>>>(dst, C, MN, (int)ksplit);
+    ctx->launches++;
+  }
+  TNCB_CUDA(cudaGetLastError());
+  return TNCB_OK;
+}
+
+template <int BN, int BM, int WN, int WM, int ST, bool BKF, bool AKF>
+static int launch_k1_cfg(tncb_ctx* ctx, const K1Args& a) {
+  auto kern = k1_kernel<BN, BM, WN, WM, ST, BKF, AKF>;
+  const size_t smem = (size_t)ST * (BN * K1_BK + K1_BK * BM) * sizeof(double2);
+  TNCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long tiles = (long long)a.tiles_m * a.tiles_n;
+  if (tiles > 0x7fffffffLL) return fail(TNCB_ERR_UNSUPPORTED, "K1 grid too large");
+  kern<<<(unsigned)tiles, WN * WM * 32, smem, ctx->stream>>>(a);
+  ctx->launches++;
+  TNCB_CUDA(cudaGetLastError());
+  return TNCB_OK;
+}
+
+template <int BN, int BM, int WN, int WM, int ST>
+static int launch_k1_modes(tncb_ctx* ctx, K1Args& a, bool bkf, bool akf) {
+  a.tiles_m = (int)((a.M + BM - 1) / BM);
+  a.tiles_n = (int)((a.N + BN - 1) / BN);
+  if (bkf && akf) return launch_k1_cfg<BN, BM, WN, WM, ST, true, true>(ctx, a);
+  if (bkf && !akf) return launch_k1_cfg<BN, BM, WN, WM, ST, true, false>(ctx, a);
+  if (!bkf && akf) return launch_k1_cfg<BN, BM, WN, WM, ST, false, true>(ctx, a);
+  return launch_k1_cfg<BN, BM, WN, WM, ST, false, false>(ctx, a);
+}
+
+static int launch_k1(tncb_ctx* ctx, const PairPlan& P, const double2* A, const double2* B, double2* C) {
+  const size_t tab_elems = (size_t)(P.M + P.N + 2 * P.K);
+  int rc = ensure_tab(ctx, tab_elems);
+  if (rc) return rc;
+  {
+    const long long total = (long long)tab_elems;
+    const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)ctx->sm_count * 8);
+    build_tables_kernel<<<blocks, 256, 0, ctx->stream>>>(P.m, P.n, P.k, P.M, P.N, P.K, ctx->tab);
+    ctx->launches++;
+  }
+  K1Args a;
+  a.A = A; a.B = B; a.C = C;
+  a.offAm = ctx->tab; a.offBn = ctx->tab + P.M; a.offAk = ctx->tab + P.M + P.N; a.offBk = a.offAk + P.K;
+  a.M = P.M; a.N = P.N; a.K = P.K;
+  const long long big_tiles = ((P.M + 63) / 64) * ((P.N + 127) / 128);
+  if (big_tiles >= 2LL * ctx->sm_count)
+    return launch_k1_modes<128, 64, 4, 2, 3>(ctx, a, P.b_kfast, P.a_kfast);
+  return launch_k1_modes<64, 64, 2, 2, 3>(ctx, a, P.b_kfast, P.a_kfast);
+}
+
+int launch_pair(tncb_ctx* ctx, const PairPlan& P, const double2* A, const double2* B, double2* C) {
+  if (P.M * P.N == 0) return TNCB_OK;
+  if (P.kernel_class == 1) return launch_k1(ctx, P, A, B, C);
+  return launch_k0(ctx, P, A, B, C);
+}
+
+int launch_permute(tncb_ctx* ctx, const double2* in, double2* out, int rank,
+                   const uint64_t* in_dims, const int* perm) {
+  std::vector<long long> istr(rank);
+  long long s = 1, total = 1;
+  for (int i = rank - 1; i >= 0; i--) { istr[i] = s; s *= (long long)in_dims[i]; }
+  total = s;
+  // output leg i walks input leg perm[i]; fuse neighbours that stay adjacent in the input
+  LegList L{}; int n = 0;
+  for (int i = 0; i < rank; i++) {
+    long long d = (long long)in_dims[perm[i]], st = istr[perm[i]];
+    if (d == 1) continue;
+    if (n > 0 && L.sa[n - 1] == st * d) { L.dim[n - 1] *= d; L.sa[n - 1] = st; continue; }
+    if (n >= kMaxGroups) return fail(TNCB_ERR_INVALID, "too many leg groups in permute");
+    L.dim[n] = d; L.sa[n] = st; L.sb[n] = 0; n++;
+  }
+  L.n = n;
+  if (total == 0) return TNCB_OK;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)ctx->sm_count * 16);
+  permute_kernel<<<blocks, 256, 0, ctx->stream>>>(in, out, L, total);
+  ctx->launches++;
+  TNCB_CUDA(cudaGetLastError());
+  return TNCB_OK;
+}
+
+int launch_conj(tncb_ctx* ctx, double2* data, uint64_t elems) {
+  if (elems == 0) return TNCB_OK;
+  const int blocks = (int)std::min<long long>(((long long)elems + 255) / 256, (long long)ctx->sm_count * 16);
+  conj_kernel<<<blocks, 256, 0, ctx->stream>>>(data, (long long)elems);
+  ctx->launches++;
+  TNCB_CUDA(cudaGetLastError());
+  return TNCB_OK;
+}
+
+} // namespace tncb

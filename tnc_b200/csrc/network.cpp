@@ -1,0 +1,302 @@
+// contract_tensor_network on the device: replaces tnc/src/tensornetwork/contraction.rs:30-88.
+//
+// The reference walks the path sequentially and, per pair, materialises the payloads
+// (tensordata.rs:40-59), allocates a result and calls tetra::contract.  Here the (nested)
+// path is first compiled from metadata alone into a flat schedule of pair plans (leg algebra
+// of tensor.rs:463-479); execution stages every leaf payload (gate tables, host matrices)
+// into pinned memory, ships them in ONE host->device copy and then enqueues all pair kernels
+// on the context stream without host round trips.  Arena memory of consumed operands is
+// recycled in stream order.
+#include "internal.h"
+#include <algorithm>
+#include <complex>
+#include <cstring>
+
+namespace tncb {
+
+int gate_matrix(const char* name, const double* ang, int n_ang, bool adjoint, std::complex<double>* out);
+
+struct SlotMeta {
+  std::vector<uint64_t> legs, dims;
+  uint64_t elems = 1;
+  int leaf_index = -1;      // >= 0: payload comes from the leaf block / a device handle
+};
+
+struct Step { int a, b, out; PairPlan plan; };
+
+struct Schedule {
+  std::vector<SlotMeta> slots;
+  std::vector<size_t> leaf_offset; // element offset of leaf i in the leaf block
+  std::vector<int> leaf_kind;
+  size_t leaf_block_elems = 0;
+  std::vector<Step> steps;
+  int result_slot = -1;
+  double flops = 0, bytes = 0;
+  size_t n_leaves_total = 0;
+};
+
+static const tncb_path* find_nested(const tncb_path* path, size_t idx) {
+  if (!path) return nullptr;
+  for (size_t q = 0; q < path->n_nested; q++)
+    if (path->nested_index[q] == idx) return &path->nested[q];
+  return nullptr;
+}
+
+static size_t count_leaves(const tncb_tn* tn) {
+  if (tn->n_children == 0) return 1;
+  size_t c = 0;
+  for (size_t i = 0; i < tn->n_children; i++) c += count_leaves(&tn->children[i]);
+  return c;
+}
+
+static int add_leaf(const tncb_tn* leaf, Schedule& S, size_t leaf_idx, int* slot_out) {
+  S.leaf_kind[leaf_idx] = leaf->kind;
+  if (leaf->kind == TNCB_DATA_UNCONTRACTED) { *slot_out = -1; return TNCB_OK; }
+  if (leaf->rank < 0 || leaf->rank > kMaxLegs) return fail(TNCB_ERR_INVALID, "leaf rank out of range");
+  SlotMeta m;
+  m.legs.assign(leaf->legs, leaf->legs + leaf->rank);
+  m.dims.assign(leaf->dims, leaf->dims + leaf->rank);
+  for (int i = 0; i < leaf->rank; i++) m.elems *= leaf->dims[i];
+  m.leaf_index = (int)leaf_idx;
+  if (leaf->kind == TNCB_DATA_GATE) {
+    if (!leaf->gate_name) return fail(TNCB_ERR_GATE, "gate leaf without a name");
+    std::complex<double> tmp[16];
+    int cnt = gate_matrix(leaf->gate_name, leaf->gate_angles, leaf->n_gate_angles, leaf->gate_adjoint != 0, tmp);
+    if (cnt < 0) return cnt;
+    if ((uint64_t)cnt != m.elems) return fail(TNCB_ERR_SHAPE, std::string("gate '") + leaf->gate_name + "' does not match the leaf's bond dimensions");
+  } else if (leaf->kind == TNCB_DATA_MATRIX) {
+    if (!leaf->host_re_im) return fail(TNCB_ERR_INVALID, "matrix leaf without host data");
+  } else if (leaf->kind == TNCB_DATA_DEVICE) {
+    if (!leaf->device) return fail(TNCB_ERR_INVALID, "device leaf without a tensor handle");
+    if (leaf->device->elems != m.elems) return fail(TNCB_ERR_SHAPE, "device leaf: element count mismatch");
+  } else {
+    return fail(TNCB_ERR_UNSUPPORTED, "unsupported TensorData kind (File payloads need HDF5)");
+  }
+  if (leaf->kind != TNCB_DATA_DEVICE) {
+    S.leaf_offset[leaf_idx] = S.leaf_block_elems;
+    S.leaf_block_elems += std::max<uint64_t>(m.elems, 1);
+  }
+  S.slots.push_back(std::move(m));
+  *slot_out = (int)S.slots.size() - 1;
+  return TNCB_OK;
+}
+
+// Returns the slot id that holds the contraction result of `tn` (-1: nothing / empty tensor).
+static int build(const tncb_tn* tn, const tncb_path* path, Schedule& S, size_t& leaf_counter, int* result) {
+  if (tn->n_children == 0) { // a leaf handed to contract_tensor_network: only an empty path is legal
+    if (path && (path->n_pairs || path->n_nested)) return fail(TNCB_ERR_INVALID, "path given for a leaf tensor");
+    return add_leaf(tn, S, leaf_counter++, result);
+  }
+  const size_t nc = tn->n_children;
+  std::vector<int> slot(nc, -1);
+  std::vector<char> uncontracted_composite(nc, 0);
+  if (path) for (size_t q = 0; q < path->n_nested; q++)
+    if (path->nested_index[q] >= nc) return fail(TNCB_ERR_INVALID, "nested path index out of range");
+  // nested paths first (contraction.rs:34-38); ascending child order
+  for (size_t i = 0; i < nc; i++) {
+    const tncb_tn* c = &tn->children[i];
+    const tncb_path* np = find_nested(path, i);
+    int rc;
+    if (c->n_children == 0) {
+      if (np && (np->n_pairs || np->n_nested)) return fail(TNCB_ERR_INVALID, "nested path given for a leaf child");
+      if ((rc = add_leaf(c, S, leaf_counter++, &slot[i]))) return rc;
+    } else if (np) {
+      if ((rc = build(c, np, S, leaf_counter, &slot[i]))) return rc;
+    } else {
+      uncontracted_composite[i] = 1; // stays TensorData::Uncontracted
+      size_t n = count_leaves(c);
+      for (size_t q = 0; q < n; q++) S.leaf_kind[leaf_counter + q] = TNCB_DATA_UNCONTRACTED;
+      leaf_counter += n;
+    }
+  }
+  const size_t np_ = path ? path->n_pairs : 0;
+  for (size_t q = 0; q < np_; q++) {
+    const uint64_t i = path->pairs[2 * q], j = path->pairs[2 * q + 1];
+    if (i >= nc || j >= nc) return fail(TNCB_ERR_INVALID, "pair (" + std::to_string(i) + "," + std::to_string(j) + ") indexes past the tensor list");
+    if (i == j || slot[i] < 0 || slot[j] < 0)
+      return fail(TNCB_ERR_UNCONTRACTED, "pair (" + std::to_string(i) + "," + std::to_string(j) + "): Cannot convert uncontracted tensor to data");
+    const SlotMeta& a = S.slots[slot[i]];
+    const SlotMeta& b = S.slots[slot[j]];
+    Step st; st.a = slot[i]; st.b = slot[j];
+    int rc = plan_pair((int)a.legs.size(), a.legs.data(), a.dims.data(), (int)b.legs.size(), b.legs.data(), b.dims.data(), st.plan);
+    if (rc) return rc;
+    SlotMeta o; o.legs = st.plan.out_legs; o.dims = st.plan.out_dims;
+    for (uint64_t d : o.dims) o.elems *= d;
+    S.slots.push_back(std::move(o));
+    st.out = (int)S.slots.size() - 1;
+    S.flops += st.plan.flops(); S.bytes += st.plan.bytes();
+    S.steps.push_back(std::move(st));
+    slot[i] = S.steps.back().out; slot[j] = -1; uncontracted_composite[j] = 0;
+  }
+  // retain(non-empty leaf or composite); at most one may remain (contraction.rs:48-51)
+  int remaining = 0, last = -1;
+  for (size_t i = 0; i < nc; i++) {
+    if (slot[i] >= 0) { remaining++; last = slot[i]; }
+    else if (uncontracted_composite[i]) { remaining++; last = -2; }
+  }
+  if (remaining > 1 || last == -2) return fail(TNCB_ERR_NOT_CONTRACTED, "Not fully contracted");
+  *result = last;
+  return TNCB_OK;
+}
+
+static int build_schedule(const tncb_tn* tn, const tncb_path* path, Schedule& S) {
+  if (!tn) return fail(TNCB_ERR_INVALID, "tn is null");
+  S.n_leaves_total = count_leaves(tn);
+  S.leaf_offset.assign(S.n_leaves_total, 0);
+  S.leaf_kind.assign(S.n_leaves_total, TNCB_DATA_UNCONTRACTED);
+  size_t counter = 0;
+  return build(tn, path, S, counter, &S.result_slot);
+}
+
+static void collect_leaf_nodes(const tncb_tn* tn, std::vector<const tncb_tn*>& v) {
+  if (tn->n_children == 0) { v.push_back(tn); return; }
+  for (size_t i = 0; i < tn->n_children; i++) collect_leaf_nodes(&tn->children[i], v);
+}
+
+static int execute(tncb_ctx* ctx, const Schedule& S, const tncb_tn* tn, tncb_tensor** out, int* n_out, uint64_t* out_legs) {
+  TNCB_CUDA(cudaSetDevice(ctx->device));
+  std::vector<const tncb_tn*> leaves;
+  collect_leaf_nodes(tn, leaves);
+  if (leaves.size() != S.n_leaves_total) return fail(TNCB_ERR_INVALID, "network does not match the plan");
+  // ---- stage all host payloads, one H2D copy ----
+  const size_t block_bytes = S.leaf_block_elems * sizeof(double2);
+  void* leaf_block = nullptr;
+  if (block_bytes) {
+    if (ctx->stage_bytes < block_bytes) {
+      if (ctx->stage_host) { TNCB_CUDA(cudaStreamSynchronize(ctx->stream)); cudaFreeHost(ctx->stage_host); ctx->stage_host = nullptr; }
+      size_t want = std::max(block_bytes, (size_t)1 << 20);
+      TNCB_CUDA(cudaMallocHost(&ctx->stage_host, want));
+      ctx->stage_bytes = want;
+    } else {
+      // the previous network's upload may still be reading the staging buffer
+      TNCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    std::complex<double>* stage = (std::complex<double>*)ctx->stage_host;
+    for (size_t li = 0; li < leaves.size(); li++) {
+      const tncb_tn* lf = leaves[li];
+      if (S.leaf_kind[li] != lf->kind) return fail(TNCB_ERR_INVALID, "network payload kinds do not match the plan");
+      if (lf->kind == TNCB_DATA_GATE) {
+        int cnt = gate_matrix(lf->gate_name, lf->gate_angles, lf->n_gate_angles, lf->gate_adjoint != 0, stage + S.leaf_offset[li]);
+        if (cnt < 0) return cnt;
+      } else if (lf->kind == TNCB_DATA_MATRIX) {
+        uint64_t e = 1; for (int i = 0; i < lf->rank; i++) e *= lf->dims[i];
+        std::memcpy(stage + S.leaf_offset[li], lf->host_re_im, e * sizeof(double2));
+      }
+    }
+    int rc = ctx->arena.alloc(block_bytes, &leaf_block);
+    if (rc) return rc;
+    TNCB_CUDA(cudaMemcpyAsync(leaf_block, ctx->stage_host, block_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  // ---- run the schedule ----
+  struct Live { double2* ptr = nullptr; size_t bytes = 0; tncb_tensor* handle = nullptr; };
+  std::vector<Live> live(S.slots.size());
+  for (size_t s = 0; s < S.slots.size(); s++) {
+    const int li = S.slots[s].leaf_index;
+    if (li < 0) continue;
+    if (S.leaf_kind[li] == TNCB_DATA_DEVICE) { live[s].ptr = leaves[li]->device->ptr; live[s].handle = leaves[li]->device; }
+    else live[s].ptr = (double2*)leaf_block + S.leaf_offset[li];
+  }
+  int rc = TNCB_OK;
+  for (const Step& st : S.steps) {
+    const SlotMeta& om = S.slots[st.out];
+    size_t bytes = std::max<size_t>(om.elems * sizeof(double2), 16);
+    void* p = nullptr;
+    if ((rc = ctx->arena.alloc(bytes, &p))) break;
+    live[st.out].ptr = (double2*)p; live[st.out].bytes = bytes;
+    if ((rc = launch_pair(ctx, st.plan, live[st.a].ptr, live[st.b].ptr, live[st.out].ptr))) break;
+    for (int s : {st.a, st.b}) { // operands are consumed (mem::take, contraction.rs:61-62)
+      if (live[s].handle) { tncb_tensor_free(ctx, live[s].handle); live[s].handle = nullptr; }
+      else if (live[s].bytes) ctx->arena.free(live[s].ptr, live[s].bytes);
+      live[s].ptr = nullptr; live[s].bytes = 0;
+    }
+  }
+  tncb_tensor* result = nullptr;
+  if (!rc && S.result_slot >= 0) {
+    const SlotMeta& rm = S.slots[S.result_slot];
+    Live& rl = live[S.result_slot];
+    result = new tncb_tensor();
+    result->rank = (int)rm.dims.size(); result->elems = rm.elems;
+    for (size_t i = 0; i < rm.dims.size(); i++) result->dims[i] = rm.dims[i];
+    if (rl.bytes) { // produced by a pair: hand the arena block over
+      result->ptr = rl.ptr; result->bytes = rl.bytes; rl.bytes = 0;
+    } else if (rl.handle) { // a device leaf that was never contracted
+      *result = *rl.handle; delete rl.handle; rl.handle = nullptr;
+    } else { // an uploaded leaf that was never contracted: copy it out of the leaf block
+      result->bytes = std::max<size_t>(rm.elems * sizeof(double2), 16);
+      void* p = nullptr;
+      rc = ctx->arena.alloc(result->bytes, &p);
+      if (!rc) {
+        result->ptr = (double2*)p;
+        cudaMemcpyAsync(p, rl.ptr, rm.elems * sizeof(double2), cudaMemcpyDeviceToDevice, ctx->stream);
+      } else { delete result; result = nullptr; }
+    }
+  }
+  // anything still live was not consumed because of an error
+  for (size_t s = 0; s < live.size(); s++)
+    if (live[s].bytes) ctx->arena.free(live[s].ptr, live[s].bytes);
+  if (leaf_block) ctx->arena.free(leaf_block, block_bytes);
+  if (rc) return rc;
+  if (out) *out = result; else if (result) tncb_tensor_free(ctx, result);
+  if (n_out) *n_out = S.result_slot >= 0 ? (int)S.slots[S.result_slot].legs.size() : 0;
+  if (out_legs && S.result_slot >= 0)
+    for (size_t i = 0; i < S.slots[S.result_slot].legs.size(); i++) out_legs[i] = S.slots[S.result_slot].legs[i];
+  return TNCB_OK;
+}
+
+} // namespace tncb
+
+struct tncb_plan { tncb::Schedule S; };
+
+extern "C" {
+
+int tncb_contract_tensor_network(tncb_ctx* ctx, const tncb_tn* tn, const tncb_path* path,
+                                 tncb_tensor** out, int* n_out, uint64_t* out_legs) {
+  if (!ctx || !tn) return tncb::fail(TNCB_ERR_INVALID, "null argument");
+  tncb::Schedule S;
+  int rc = tncb::build_schedule(tn, path, S);
+  if (rc) return rc;
+  return tncb::execute(ctx, S, tn, out, n_out, out_legs);
+}
+
+int tncb_plan_create(tncb_ctx* ctx, const tncb_tn* tn, const tncb_path* path, tncb_plan** out) {
+  (void)ctx;
+  if (!tn || !out) return tncb::fail(TNCB_ERR_INVALID, "null argument");
+  tncb_plan* p = new tncb_plan();
+  int rc = tncb::build_schedule(tn, path, p->S);
+  if (rc) { delete p; return rc; }
+  *out = p;
+  return TNCB_OK;
+}
+
+int tncb_plan_execute(tncb_ctx* ctx, tncb_plan* plan, const tncb_tn* tn, tncb_tensor** out, int* n_out, uint64_t* out_legs) {
+  if (!ctx || !plan || !tn) return tncb::fail(TNCB_ERR_INVALID, "null argument");
+  return tncb::execute(ctx, plan->S, tn, out, n_out, out_legs);
+}
+
+int tncb_plan_info(const tncb_plan* plan, uint64_t* n_pairs, double* flops, double* bytes, uint64_t* peak_bytes, uint64_t* n_kernels) {
+  if (!plan) return tncb::fail(TNCB_ERR_INVALID, "plan is null");
+  const tncb::Schedule& S = plan->S;
+  if (n_pairs) *n_pairs = S.steps.size();
+  if (flops) *flops = S.flops;
+  if (bytes) *bytes = S.bytes;
+  if (peak_bytes) { // replay the liveness: leaves + live intermediates
+    size_t live = S.leaf_block_elems * 16, peak = live;
+    std::vector<size_t> sz(S.slots.size(), 0);
+    for (const tncb::Step& st : S.steps) {
+      sz[st.out] = std::max<size_t>(S.slots[st.out].elems * 16, 256);
+      live += sz[st.out]; peak = std::max(peak, live);
+      live -= sz[st.a] + sz[st.b]; sz[st.a] = sz[st.b] = 0;
+    }
+    *peak_bytes = peak;
+  }
+  if (n_kernels) {
+    uint64_t k = 0;
+    for (const tncb::Step& st : S.steps) k += st.plan.kernel_class == 1 ? 2 : 1;
+    *n_kernels = k;
+  }
+  return TNCB_OK;
+}
+
+void tncb_plan_destroy(tncb_plan* plan) { delete plan; }
+
+} // extern "C"

@@ -1,0 +1,284 @@
+// Context, device arena, tensor handles and the single-pair entry points of libtncb200.
+#include "internal.h"
+#include <algorithm>
+#include <cstring>
+
+namespace tncb {
+
+// ---- arena: first-fit free lists over cudaMalloc'd slabs, 256-byte granularity --------------
+static inline size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int Arena::alloc(size_t bytes, void** out) {
+  bytes = round_up(std::max<size_t>(bytes, 256), 256);
+  for (Slab& s : slabs) {
+    for (auto it = s.free_by_off.begin(); it != s.free_by_off.end(); ++it) {
+      if (it->second >= bytes) {
+        size_t off = it->first, sz = it->second;
+        s.free_by_off.erase(it);
+        if (sz > bytes) s.free_by_off[off + bytes] = sz - bytes;
+        *out = s.base + off;
+        live += bytes; peak = std::max(peak, live);
+        return TNCB_OK;
+      }
+    }
+  }
+  // new slab
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return fail(TNCB_ERR_CUDA, "cudaMemGetInfo failed");
+  size_t limit = capacity_limit ? capacity_limit : reserved + (free_b > ((size_t)1 << 30) ? free_b - ((size_t)1 << 30) : 0);
+  if (reserved + bytes > limit)
+    return fail(TNCB_ERR_OOM, "device arena exhausted: need " + std::to_string(bytes) + " B, reserved " +
+                                  std::to_string(reserved) + " B, limit " + std::to_string(limit) + " B");
+  size_t want = std::max(bytes, std::min(next_slab, limit - reserved));
+  want = round_up(want, (size_t)2 << 20);
+  if (reserved + want > limit) want = bytes;
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, want);
+  if (e != cudaSuccess && want > bytes) { cudaGetLastError(); want = bytes; e = cudaMalloc(&p, want); }
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(TNCB_ERR_OOM, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+  reserved += want;
+  next_slab = std::min(next_slab * 2, (size_t)16 << 30);
+  Slab s; s.base = (char*)p; s.size = want;
+  if (want > bytes) s.free_by_off[bytes] = want - bytes;
+  slabs.push_back(std::move(s));
+  *out = p;
+  live += bytes; peak = std::max(peak, live);
+  return TNCB_OK;
+}
+
+void Arena::free(void* p, size_t bytes) {
+  if (!p) return;
+  bytes = round_up(std::max<size_t>(bytes, 256), 256);
+  for (Slab& s : slabs) {
+    if ((char*)p >= s.base && (char*)p < s.base + s.size) {
+      size_t off = (char*)p - s.base;
+      auto it = s.free_by_off.emplace(off, bytes).first;
+      // coalesce with next
+      auto nx = std::next(it);
+      if (nx != s.free_by_off.end() && it->first + it->second == nx->first) { it->second += nx->second; s.free_by_off.erase(nx); }
+      if (it != s.free_by_off.begin()) {
+        auto pv = std::prev(it);
+        if (pv->first + pv->second == it->first) { pv->second += it->second; s.free_by_off.erase(it); }
+      }
+      live -= bytes;
+      return;
+    }
+  }
+}
+
+void Arena::release_all() {
+  for (Slab& s : slabs) cudaFree(s.base);
+  slabs.clear(); reserved = live = 0;
+}
+
+int tensor_new(tncb_ctx* ctx, int rank, const uint64_t* dims, tncb_tensor** out) {
+  if (rank < 0 || rank > kMaxLegs) return fail(TNCB_ERR_INVALID, "tensor rank out of range");
+  tncb_tensor* t = new tncb_tensor();
+  t->rank = rank; t->elems = 1;
+  for (int i = 0; i < rank; i++) { t->dims[i] = dims[i]; t->elems *= dims[i]; }
+  t->bytes = std::max<size_t>(t->elems * sizeof(double2), 16);
+  void* p = nullptr;
+  int rc = ctx->arena.alloc(t->bytes, &p);
+  if (rc) { delete t; return rc; }
+  t->ptr = (double2*)p;
+  *out = t;
+  return TNCB_OK;
+}
+
+} // namespace tncb
+
+using namespace tncb;
+
+extern "C" {
+
+int tncb_ctx_create(int device, size_t arena_bytes, tncb_ctx** out) {
+  if (!out) return fail(TNCB_ERR_INVALID, "out is null");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    return fail(TNCB_ERR_CUDA, std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                                   "); libtncb200 has no CPU fallback");
+  }
+  if (device < 0 || device >= count) return fail(TNCB_ERR_INVALID, "device index out of range");
+  TNCB_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  TNCB_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(TNCB_ERR_CUDA, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+                                   ", libtncb200 is built for sm_100a only");
+  tncb_ctx* ctx = new tncb_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->arena.capacity_limit = arena_bytes;
+  cudaError_t se = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (se != cudaSuccess) { delete ctx; return fail(TNCB_ERR_CUDA, cudaGetErrorString(se)); }
+  // keep freed workspace memory in the stream-ordered pool
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t thr = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  *out = ctx;
+  return TNCB_OK;
+}
+
+void tncb_ctx_destroy(tncb_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  tncb_comm_destroy(ctx);
+  if (ctx->tab) cudaFree(ctx->tab);
+  if (ctx->partial) cudaFree(ctx->partial);
+  if (ctx->stage_host) cudaFreeHost(ctx->stage_host);
+  ctx->arena.release_all();
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int tncb_ctx_synchronize(tncb_ctx* ctx) {
+  if (!ctx) return fail(TNCB_ERR_INVALID, "ctx is null");
+  TNCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TNCB_OK;
+}
+
+void* tncb_ctx_stream(tncb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int tncb_ctx_stats(tncb_ctx* ctx, uint64_t* kernel_launches, uint64_t* arena_peak_bytes, uint64_t* arena_live_bytes) {
+  if (!ctx) return fail(TNCB_ERR_INVALID, "ctx is null");
+  if (kernel_launches) *kernel_launches = ctx->launches;
+  if (arena_peak_bytes) *arena_peak_bytes = ctx->arena.peak;
+  if (arena_live_bytes) *arena_live_bytes = ctx->arena.live;
+  return TNCB_OK;
+}
+
+int tncb_ctx_reset_stats(tncb_ctx* ctx) {
+  if (!ctx) return fail(TNCB_ERR_INVALID, "ctx is null");
+  ctx->launches = 0; ctx->arena.peak = ctx->arena.live;
+  return TNCB_OK;
+}
+
+int tncb_tensor_alloc(tncb_ctx* ctx, int rank, const uint64_t* dims, tncb_tensor** out) {
+  if (!ctx || !out || (rank > 0 && !dims)) return fail(TNCB_ERR_INVALID, "null argument");
+  TNCB_CUDA(cudaSetDevice(ctx->device));
+  return tensor_new(ctx, rank, dims, out);
+}
+
+int tncb_tensor_upload(tncb_ctx* ctx, int rank, const uint64_t* dims, const double* host, tncb_tensor** out) {
+  if (!host) return fail(TNCB_ERR_INVALID, "host buffer is null");
+  int rc = tncb_tensor_alloc(ctx, rank, dims, out);
+  if (rc) return rc;
+  tncb_tensor* t = *out;
+  // pageable or pinned host memory both work; the copy is ordered on the ctx stream
+  TNCB_CUDA(cudaMemcpyAsync(t->ptr, host, t->elems * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
+  TNCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TNCB_OK;
+}
+
+int tncb_tensor_download(tncb_ctx* ctx, const tncb_tensor* t, double* host) {
+  if (!ctx || !t || !host) return fail(TNCB_ERR_INVALID, "null argument");
+  TNCB_CUDA(cudaSetDevice(ctx->device));
+  TNCB_CUDA(cudaMemcpyAsync(host, t->ptr, t->elems * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
+  TNCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TNCB_OK;
+}
+
+int tncb_tensor_free(tncb_ctx* ctx, tncb_tensor* t) {
+  if (!t) return TNCB_OK;
+  if (!ctx) return fail(TNCB_ERR_INVALID, "ctx is null");
+  // Stream-ordered reuse: every kernel of this ctx runs on ctx->stream, so a later
+  // allocation of the same bytes is only ever touched by later kernels.
+  if (t->owned && t->ptr) ctx->arena.free(t->ptr, t->bytes);
+  delete t;
+  return TNCB_OK;
+}
+
+int tncb_tensor_rank(const tncb_tensor* t) { return t ? t->rank : TNCB_ERR_INVALID; }
+int tncb_tensor_dims(const tncb_tensor* t, uint64_t* dims_out) {
+  if (!t || !dims_out) return fail(TNCB_ERR_INVALID, "null argument");
+  for (int i = 0; i < t->rank; i++) dims_out[i] = t->dims[i];
+  return TNCB_OK;
+}
+uint64_t tncb_tensor_elements(const tncb_tensor* t) { return t ? t->elems : 0; }
+void* tncb_tensor_device_ptr(const tncb_tensor* t) { return t ? (void*)t->ptr : nullptr; }
+
+static int check_tensor_legs(const tncb_tensor* t, int n, const char* who) {
+  if (!t) return fail(TNCB_ERR_UNCONTRACTED, std::string("tensor ") + who + " is null");
+  if (n != t->rank) return fail(TNCB_ERR_INVALID, std::string("leg count of ") + who + " != tensor rank");
+  return TNCB_OK;
+}
+
+int tncb_contract_pair_into(tncb_ctx* ctx, int n_a, const uint64_t* a_legs, const tncb_tensor* a,
+                            int n_b, const uint64_t* b_legs, const tncb_tensor* b, tncb_tensor* out) {
+  if (!ctx || !out) return fail(TNCB_ERR_INVALID, "null argument");
+  int rc;
+  if ((rc = check_tensor_legs(a, n_a, "a")) || (rc = check_tensor_legs(b, n_b, "b"))) return rc;
+  TNCB_CUDA(cudaSetDevice(ctx->device));
+  PairPlan P;
+  if ((rc = plan_pair(n_a, a_legs, a->dims, n_b, b_legs, b->dims, P))) return rc;
+  if ((uint64_t)(P.M * P.N) != out->elems) return fail(TNCB_ERR_SHAPE, "output tensor has the wrong number of elements");
+  return launch_pair(ctx, P, a->ptr, b->ptr, out->ptr);
+}
+
+int tncb_contract_pair_keep(tncb_ctx* ctx, int n_a, const uint64_t* a_legs, const tncb_tensor* a,
+                            int n_b, const uint64_t* b_legs, const tncb_tensor* b, tncb_tensor** out) {
+  if (!ctx || !out) return fail(TNCB_ERR_INVALID, "null argument");
+  int rc;
+  if ((rc = check_tensor_legs(a, n_a, "a")) || (rc = check_tensor_legs(b, n_b, "b"))) return rc;
+  TNCB_CUDA(cudaSetDevice(ctx->device));
+  PairPlan P;
+  if ((rc = plan_pair(n_a, a_legs, a->dims, n_b, b_legs, b->dims, P))) return rc;
+  tncb_tensor* c = nullptr;
+  if ((rc = tensor_new(ctx, (int)P.out_dims.size(), P.out_dims.data(), &c))) return rc;
+  if ((rc = launch_pair(ctx, P, a->ptr, b->ptr, c->ptr))) { tncb_tensor_free(ctx, c); return rc; }
+  *out = c;
+  return TNCB_OK;
+}
+
+int tncb_contract_pair(tncb_ctx* ctx, int n_out, const uint64_t* out_legs,
+                       int n_a, const uint64_t* a_legs, tncb_tensor* a,
+                       int n_b, const uint64_t* b_legs, tncb_tensor* b, tncb_tensor** out) {
+  if (!ctx || !out) return fail(TNCB_ERR_INVALID, "null argument");
+  int rc;
+  if ((rc = check_tensor_legs(a, n_a, "a")) || (rc = check_tensor_legs(b, n_b, "b"))) return rc;
+  if (a == b) return fail(TNCB_ERR_INVALID, "a and b are the same tensor");
+  if (out_legs) {
+    PairPlan P;
+    if ((rc = plan_pair(n_a, a_legs, a->dims, n_b, b_legs, b->dims, P))) return rc;
+    bool same = (int)P.out_legs.size() == n_out;
+    for (int i = 0; same && i < n_out; i++) same = P.out_legs[i] == out_legs[i];
+    if (!same) return fail(TNCB_ERR_INVALID, "out_legs must equal (b \\ a) ++ (a \\ b)");
+  }
+  rc = tncb_contract_pair_keep(ctx, n_a, a_legs, a, n_b, b_legs, b, out);
+  if (rc) return rc;
+  // ownership moved to the callee, exactly like the Rust by-value call (contraction.rs:78-84)
+  tncb_tensor_free(ctx, a);
+  tncb_tensor_free(ctx, b);
+  return TNCB_OK;
+}
+
+int tncb_permute(tncb_ctx* ctx, tncb_tensor* t, const int* perm, tncb_tensor** out) {
+  if (!ctx || !t || !out || (t->rank > 0 && !perm)) return fail(TNCB_ERR_INVALID, "null argument");
+  TNCB_CUDA(cudaSetDevice(ctx->device));
+  bool seen[kMaxLegs] = {false};
+  uint64_t odims[kMaxLegs];
+  for (int i = 0; i < t->rank; i++) {
+    if (perm[i] < 0 || perm[i] >= t->rank || seen[perm[i]]) return fail(TNCB_ERR_INVALID, "perm is not a permutation");
+    seen[perm[i]] = true; odims[i] = t->dims[perm[i]];
+  }
+  tncb_tensor* o = nullptr;
+  int rc = tensor_new(ctx, t->rank, odims, &o);
+  if (rc) return rc;
+  if ((rc = launch_permute(ctx, t->ptr, o->ptr, t->rank, t->dims, perm))) { tncb_tensor_free(ctx, o); return rc; }
+  tncb_tensor_free(ctx, t);
+  *out = o;
+  return TNCB_OK;
+}
+
+int tncb_conjugate(tncb_ctx* ctx, tncb_tensor* t) {
+  if (!ctx || !t) return fail(TNCB_ERR_INVALID, "null argument");
+  TNCB_CUDA(cudaSetDevice(ctx->device));
+  return launch_conj(ctx, t->ptr, t->elems);
+}
+
+} // extern "C"
