@@ -76,7 +76,7 @@ class DeviceTensor:
 
     @classmethod
     def from_numpy(cls, ctx: Context, arr: np.ndarray) -> "DeviceTensor":
-        a = np.ascontiguousarray(arr, dtype=np.complex128)
+        a = np.asarray(arr, dtype=np.complex128, order="C")  # (ascontiguousarray would promote 0-d to 1-d)
         h = C.c_void_p()
         check(ctx._l.tncb_tensor_upload(ctx.handle, a.ndim, u64_array(a.shape), a.ctypes.data_as(C.c_void_p), C.byref(h)))
         return cls(ctx, h, a.shape)

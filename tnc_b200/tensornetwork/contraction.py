@@ -58,7 +58,7 @@ class _Marshal:
                 node.device = m.handle
                 self.device_inputs.append(m)
             else:
-                a = np.ascontiguousarray(m, dtype=np.complex128)
+                a = np.asarray(m, dtype=np.complex128, order="C")
                 if list(a.shape) != list(t.bond_dims):
                     a = a.reshape(t.bond_dims)
                 self.keep.append(a)
