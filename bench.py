@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py -- the driver's measurement contract for the pairwise-contraction hot path.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload pair]
+
+Workload at every N: BASELINE.json configs[1] ("C2"): ONE pairwise contraction of two rank-12,
+dim-4 complex128 tensors (2^24 elements = 256 MiB each) whose 6 shared legs are interleaved
+with the free legs in both operands (so the reference's TTGT must permute both), i.e. an
+effective 4096 x 4096 x 4096 ZGEMM.  A "step" is one such contraction.  With N > 1 every rank
+contracts its own independent pair (the path's units are independent -> weak scaling, no
+data-path collective); the partitioned-network fan-in over NCCL is reported separately in the
+"partitioned" object (added when the fan-in module is present).
+
+Keys beyond the base contract: "roofline" (FP64 tensor pipe, measured DMMA peak),
+"cpu_baseline" (oracle TTGT with torch-CPU MKL zgemm on this box's host cores), "e2e"
+(host pinned buffers -> H2D -> contract -> D2H through the C ABI), "zgemm_tflops".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "pairwise contractions/sec (effective ZGEMM TFLOP/s in zgemm_tflops)"
+# Measured on this pool's B200 with tools/fp64_peak.cu (profiles/r01_fp64_peak_microbench.txt):
+# DMMA m8n8k4 sustained, = 148 SM x 64 FMA/clk x 2 x 1.965 GHz.  tcgen05 has no f64 kind.
+FP64_TENSOR_PEAK_TFLOPS = 37.2
+
+
+def c2_problem():
+    """A legs [0..11]; shared legs at A's odd positions; in B they sit at the
+    even positions in reversed order (different relative order -> both need a permute)."""
+    a_legs = list(range(12))
+    shared = [11, 9, 7, 5, 3, 1]
+    b_legs = [x for p in zip(shared, range(12, 18)) for x in p]
+    dims = [4] * 12
+    return a_legs, dims, b_legs, dims
+
+
+def pinned_complex(shape, rng):
+    import torch
+    n = int(np.prod(shape))
+    t = torch.empty(n, dtype=torch.complex128, pin_memory=torch.cuda.is_available())
+    a = t.numpy()
+    a.real[:] = rng.random(n) * 2 - 1
+    a.imag[:] = rng.random(n) * 2 - 1
+    return t, a.reshape(shape)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.06] or [r for (_, r) in self.rows]
+        for r in rows:
+            p = [x.strip() for x in r.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1])); pw.append(float(p[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[3:7]):
+                if v == "Active":
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_pair_seconds(a_legs, a, b_legs, b, repeats):
+    """The oracle's TTGT restatement with torch-CPU (MKL zgemm), all host threads."""
+    import torch
+    from oracle import tnc_oracle as orc
+    ta, tb_ = torch.from_numpy(a), torch.from_numpy(b)
+    ts = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        orc.contract_pair(a_legs, ta, b_legs, tb_, backend="torch")
+        ts.append(time.perf_counter() - t0)
+    return ts
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path for the same pair.  The Rust crate cannot be
+    built here (no cargo; tetra/HPTT/faer are un-vendored git deps), so this times the oracle
+    port: permute -> contiguous -> reshape -> MKL zgemm, all host threads (kind = "port")."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    a_legs, a_dims, b_legs, b_dims = c2_problem()
+    rng = np.random.default_rng(20240612)
+    _, a = pinned_complex(a_dims, rng)
+    _, b = pinned_complex(b_dims, rng)
+    cpu_pair_seconds(a_legs, a, b_legs, b, max(1, args.warmup))
+    ts = cpu_pair_seconds(a_legs, a, b_legs, b, args.steps)
+    sec = float(np.mean(ts))
+    flops = 8.0 * 4096 ** 3
+    val = 1.0 / sec
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "contractions/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "complex128 (f64)", "data": "synthetic",
+        "zgemm_tflops": flops / sec * 1e-12,
+        "config": {"workload": "C2: single pairwise contraction, rank-12 dim-4 operands, M=N=K=4096, interleaved shared legs"},
+        "cpu_baseline": {"value": val, "unit": "contractions/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} full C2 pairs (oracle TTGT, torch-CPU MKL zgemm, {torch.get_num_threads()} threads)",
+                         "zgemm_tflops": flops / sec * 1e-12},
+        "e2e": {"value": val, "unit": "contractions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import tnc_b200 as tb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: tnc_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    ctx = tb.Context(local)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=local)
+    a_legs, a_dims, b_legs, b_dims = c2_problem()
+    M = N = K = 4096
+    flops = 8.0 * M * N * K
+    alg_bytes = 16.0 * (M * K + K * N + M * N)
+    rng = np.random.default_rng(20240612 + rank)
+    ta, a = pinned_complex(a_dims, rng)
+    tb_, b = pinned_complex(b_dims, rng)
+    tc, c_host = pinned_complex([4] * 12, np.random.default_rng(0))
+    dA = tb.DeviceTensor.from_numpy(ctx, a)
+    dB = tb.DeviceTensor.from_numpy(ctx, b)
+    dC = tb.DeviceTensor.empty(ctx, [4] * 12)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        ctx.synchronize()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: inputs already in HBM ------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        tb.contract_pair_into(ctx, a_legs, dA, b_legs, dB, dC)
+    ctx.synchronize()
+    ctx.reset_stats()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    sampler = ClockSampler(local)
+    time.sleep(0.15)
+    t_wall0 = time.time()
+    evs[0].record(stream)
+    for i in range(args.steps):
+        tb.contract_pair_into(ctx, a_legs, dA, b_legs, dB, dC)
+        evs[i + 1].record(stream)
+    ctx.synchronize()
+    torch.cuda.synchronize()
+    t_wall1 = time.time()
+    barrier()
+    clocks = sampler.stop(t_wall0, t_wall1)
+    launches = ctx.stats()["kernel_launches"]
+    total_ms = evs[0].elapsed_time(evs[-1])
+    per = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
+    if world > 1:
+        t = torch.tensor([total_ms], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+        lt = torch.tensor([float(launches)], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
+    ms_per_step = total_ms / args.steps
+    value = world * args.steps / (total_ms * 1e-3)
+    kern_ms = float(np.mean(per))  # one K1 launch per step (offset tables are cached in the plan)
+
+    # ---- end to end through the C ABI with host buffers ------------------------------------
+    if args.kernel_only:
+        if rank == 0:
+            print(json.dumps({"kernel_ms": kern_ms, "tflops": flops / (kern_ms * 1e-3) * 1e-12,
+                              "frac": flops / (kern_ms * 1e-3) * 1e-12 / FP64_TENSOR_PEAK_TFLOPS, "clocks": clocks}), flush=True)
+        return
+    e2e_steps = max(3, min(args.steps, 10))
+    def e2e_step():
+        tb.upload_into(ctx, a, dA)
+        tb.upload_into(ctx, b, dB)
+        tb.contract_pair_into(ctx, a_legs, dA, b_legs, dB, dC)
+        tb.download_into(ctx, dC, c_host)
+    e2e_step(); ctx.synchronize()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record(stream)
+    ctx.synchronize(); torch.cuda.synchronize()
+    e2e_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_val = world * e2e_steps / (e2e_ms * 1e-3)
+    checksum = complex(c_host.reshape(-1)[:4096].sum())
+
+    line = None
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            cpu_pair_seconds(a_legs, a, b_legs, b, 1)
+            ts = cpu_pair_seconds(a_legs, a, b_legs, b, 5)
+            sec = float(np.mean(ts))
+            cpu = {"value": 1.0 / sec, "unit": "contractions/s", "cores": cores, "kind": "port",
+                   "sample": "5 full C2 pairs after 1 warm-up (oracle TTGT: permute+contiguous+MKL zgemm via torch-CPU)",
+                   "zgemm_tflops": flops / sec * 1e-12, "ms_per_pair": sec * 1e3}
+        ach = flops / (kern_ms * 1e-3) * 1e-12
+        line = {
+            "metric": METRIC, "value": value, "unit": "contractions/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "complex128 (f64)", "data": "synthetic",
+            "zgemm_tflops": world * flops / (ms_per_step * 1e-3) * 1e-12,
+            "config": {"workload": "C2: single pairwise contraction, rank-12 dim-4 operands, M=N=K=4096, interleaved shared legs",
+                       "per_rank": "one independent pair per rank", "l2": "no flush needed: operands+result 768 MiB > 126 MB L2",
+                       "kernel": "K1 fused gather + DMMA ZGEMM, 1 launch/step"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": "contractions/s", "h2d_bytes_per_step": int(2 * 16 * 4 ** 12),
+                    "d2h_bytes_per_step": int(16 * 4 ** 12), "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
+                    "result_checksum": [checksum.real, checksum.imag]},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "achieved": ach, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s",
+                         "frac": ach / FP64_TENSOR_PEAK_TFLOPS, "traffic": None,
+                         "peak_source": "measured FP64 DMMA peak on this pool (tools/fp64_peak.cu, profiles/r01_fp64_peak_microbench.txt); "
+                                        "MEASURED_PEAKS.json has no FP64 figure and tcgen05 has no f64 kind",
+                         "kernel_ms": kern_ms, "algorithmic_flops": flops, "algorithmic_bytes": alg_bytes,
+                         "hbm_frac_of_measured": alg_bytes / (kern_ms * 1e-3) / 1e9 / _hbm_peak()},
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def _hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"])
+    except Exception:
+        return 6650.0  # B200_PROFILING.md fallback
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="pair")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-only", action="store_true", help="tuning aid: skip the e2e and CPU legs")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

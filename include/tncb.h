@@ -76,6 +76,10 @@ int tncb_tensor_upload(tncb_ctx* ctx, int rank, const uint64_t* dims,
                        const double* host_re_im, tncb_tensor** out);
 int tncb_tensor_alloc(tncb_ctx* ctx, int rank, const uint64_t* dims, tncb_tensor** out);
 int tncb_tensor_download(tncb_ctx* ctx, const tncb_tensor* t, double* host_re_im);
+/* Asynchronous variants on the ctx stream (host buffer should be pinned; the caller
+ * synchronises with tncb_ctx_synchronize before touching it). */
+int tncb_tensor_write(tncb_ctx* ctx, tncb_tensor* t, const double* host_re_im);
+int tncb_tensor_read(tncb_ctx* ctx, const tncb_tensor* t, double* host_re_im);
 int tncb_tensor_free(tncb_ctx* ctx, tncb_tensor* t);
 int tncb_tensor_rank(const tncb_tensor* t);
 int tncb_tensor_dims(const tncb_tensor* t, uint64_t* dims_out);

@@ -16,7 +16,7 @@ import numpy as np
 
 from ._lib import TncbError, check, lib, u64_array
 
-__all__ = ["Context", "DeviceTensor", "TncbError", "contract_pair", "default_context", "lib"]
+__all__ = ["Context", "DeviceTensor", "TncbError", "contract_pair", "contract_pair_into", "default_context", "lib"]
 
 
 class Context:
@@ -135,3 +135,20 @@ def contract_pair(ctx: Context, a_legs, a, b_legs, b):
     da.release(); db.release()
     out = DeviceTensor.adopt(ctx, h)
     return out_legs, out.to_numpy()
+
+
+def contract_pair_into(ctx: Context, a_legs, da: DeviceTensor, b_legs, db: DeviceTensor, dc: DeviceTensor) -> None:
+    """Device-resident pair into a pre-allocated output (operands stay alive); asynchronous on
+    the context stream."""
+    check(ctx._l.tncb_contract_pair_into(ctx.handle, len(a_legs), u64_array(a_legs), da.handle,
+                                         len(b_legs), u64_array(b_legs), db.handle, dc.handle))
+
+
+def upload_into(ctx: Context, host: np.ndarray, dst: DeviceTensor) -> None:
+    """Asynchronous H2D of a (pinned) host array into an existing device tensor."""
+    check(ctx._l.tncb_tensor_write(ctx.handle, dst.handle, host.ctypes.data_as(C.c_void_p)))
+
+
+def download_into(ctx: Context, src: DeviceTensor, host: np.ndarray) -> None:
+    """Asynchronous D2H into a (pinned) host array; synchronise the context before reading."""
+    check(ctx._l.tncb_tensor_read(ctx.handle, src.handle, host.ctypes.data_as(C.c_void_p)))

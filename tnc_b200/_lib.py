@@ -61,6 +61,8 @@ SIGNATURES = {
     "tncb_tensor_upload": (C.c_int, [C.c_void_p, C.c_int, u64p, C.c_void_p, vpp]),
     "tncb_tensor_alloc": (C.c_int, [C.c_void_p, C.c_int, u64p, vpp]),
     "tncb_tensor_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tncb_tensor_write": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tncb_tensor_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "tncb_tensor_free": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tncb_tensor_rank": (C.c_int, [C.c_void_p]),
     "tncb_tensor_dims": (C.c_int, [C.c_void_p, u64p]),

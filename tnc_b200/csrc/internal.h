@@ -80,6 +80,9 @@ struct tncb_ctx {
   void* stage_host = nullptr; size_t stage_bytes = 0;
   // K1 offset-table workspace (grown on demand, stream-ordered reuse)
   long long* tab = nullptr; size_t tab_elems = 0;
+  // signature of the tables currently in `tab` (they depend on the plan only, like a TMA
+  // descriptor): an identical consecutive pair re-uses them without a rebuild
+  bool tab_valid = false; tncb::LegList tab_m{}, tab_n{}, tab_k{};
   // split-K partial workspace
   double2* partial = nullptr; size_t partial_elems = 0;
   // NCCL

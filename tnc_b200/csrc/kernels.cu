@@ -161,17 +161,30 @@ struct K1Args {
 // conflict-free 512-byte LDS.128 per warp:
 //   row operand Bt (rows n, cols k):  slot = ((n/8)*(BK/4) + k/4)*32 + (n%8)*4 + k%4
 //   col operand At (rows k, cols m):  slot = ((k/4)*(BM/8) + m/8)*32 + (m%8)*4 + k%4
+//
+// Loader mapping (per operand, chosen by the planner from the operand's strides):
+//   KFAST  : consecutive threads walk the K index   -> thread owns kk = tid%BK, rows tid/BK + (NT/BK)*j
+//   !KFAST : consecutive threads walk the free index -> warp w owns kk in [w*BK/NW, (w+1)*BK/NW),
+//            lane l owns rows l + 32*j
+// so a thread needs only 1 (KFAST) or BK/NW (!KFAST) K-offsets per chunk.  Those offsets are
+// prefetched one chunk ahead into registers and the cp.async gathers of stage kc+STAGES-1 are
+// issued in the middle of chunk kc's DMMA stream, so no table load sits on the critical path
+// (ncu r01: 20 % long_scoreboard on exactly those loads before this change).
 template <int BN, int BM, int WARPS_N, int WARPS_M, int STAGES, bool B_KFAST, bool A_KFAST>
 __global__ void __launch_bounds__(WARPS_N* WARPS_M * 32)
 k1_kernel(const __grid_constant__ K1Args p) {
   constexpr int BK = K1_BK;
-  constexpr int NT = WARPS_N * WARPS_M * 32;
+  constexpr int NW = WARPS_N * WARPS_M;
+  constexpr int NT = NW * 32;
   constexpr int TI = BN / WARPS_N / 8; // 8-row blocks per warp
   constexpr int TJ = BM / WARPS_M / 8; // 8-col blocks per warp
-  constexpr int B_EPT = BN * BK / NT;
-  constexpr int A_EPT = BK * BM / NT;
+  constexpr int KPW = BK / NW;         // kk per warp in !KFAST mode
+  static_assert(BK % NW == 0 && BN % 32 == 0 && BM % 32 == 0 && NT % BK == 0, "tile/threads mismatch");
+  constexpr int B_ROWS = B_KFAST ? BN / (NT / BK) : BN / 32; // free-index positions per thread
+  constexpr int A_COLS = A_KFAST ? BM / (NT / BK) : BM / 32;
+  constexpr int B_KO = B_KFAST ? 1 : KPW;                    // K positions per thread
+  constexpr int A_KO = A_KFAST ? 1 : KPW;
   constexpr int STAGE_ELEMS = BN * BK + BK * BM;
-  static_assert(BN * BK % NT == 0 && BK * BM % NT == 0, "tile/threads mismatch");
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2* smem = reinterpret_cast<double2*>(smem_raw);
@@ -199,48 +212,65 @@ k1_kernel(const __grid_constant__ K1Args p) {
   const long long n0 = (long long)tn * BN;
   const long long m0 = (long long)tm * BM;
 
-  // per-thread gather rows/cols (constant over the K loop)
-  long long b_off[B_EPT]; int b_slot[B_EPT]; int b_kk[B_EPT]; bool b_ok[B_EPT];
+  // ---- per-thread gather geometry (constant over the K loop) ----
+  long long b_off[B_ROWS]; bool b_ok[B_ROWS]; int b_rslot[B_ROWS];
+  int b_kk[B_KO], b_kslot[B_KO];
 #pragma unroll
-  for (int j = 0; j < B_EPT; j++) {
-    const int e = tid + j * NT;
-    const int kk = B_KFAST ? (e % BK) : (e / BN);
-    const int row = B_KFAST ? (e / BK) : (e % BN);
+  for (int j = 0; j < B_ROWS; j++) {
+    const int row = B_KFAST ? (tid / BK + (NT / BK) * j) : (lane + 32 * j);
     const long long gn = n0 + row;
     b_ok[j] = gn < p.N;
     b_off[j] = __ldg(p.offBn + (b_ok[j] ? gn : 0));
-    b_kk[j] = kk;
-    b_slot[j] = ((row >> 3) * (BK / 4) + (kk >> 2)) * 32 + (row & 7) * 4 + (kk & 3);
+    b_rslot[j] = (row >> 3) * (BK / 4) * 32 + (row & 7) * 4;
   }
-  long long a_off[A_EPT]; int a_slot[A_EPT]; int a_kk[A_EPT]; bool a_ok[A_EPT];
 #pragma unroll
-  for (int j = 0; j < A_EPT; j++) {
-    const int e = tid + j * NT;
-    const int kk = A_KFAST ? (e % BK) : (e / BM);
-    const int col = A_KFAST ? (e / BK) : (e % BM);
+  for (int q = 0; q < B_KO; q++) {
+    b_kk[q] = B_KFAST ? (tid % BK) : (warp * KPW + q);
+    b_kslot[q] = (b_kk[q] >> 2) * 32 + (b_kk[q] & 3);
+  }
+  long long a_off[A_COLS]; bool a_ok[A_COLS]; int a_cslot[A_COLS];
+  int a_kk[A_KO], a_kslot[A_KO];
+#pragma unroll
+  for (int j = 0; j < A_COLS; j++) {
+    const int col = A_KFAST ? (tid / BK + (NT / BK) * j) : (lane + 32 * j);
     const long long gm = m0 + col;
     a_ok[j] = gm < p.M;
     a_off[j] = __ldg(p.offAm + (a_ok[j] ? gm : 0));
-    a_kk[j] = kk;
-    a_slot[j] = BN * BK + ((kk >> 2) * (BM / 8) + (col >> 3)) * 32 + (col & 7) * 4 + (kk & 3);
+    a_cslot[j] = BN * BK + (col >> 3) * 32 + (col & 7) * 4;
+  }
+#pragma unroll
+  for (int q = 0; q < A_KO; q++) {
+    a_kk[q] = A_KFAST ? (tid % BK) : (warp * KPW + q);
+    a_kslot[q] = (a_kk[q] >> 2) * (BM / 8) * 32 + (a_kk[q] & 3);
   }
 
-  auto load_stage = [&](int stage, long long k0) {
+  long long b_ko[B_KO], a_ko[A_KO]; bool b_kok[B_KO], a_kok[A_KO];
+  auto fetch_ko = [&](long long k0) {
+#pragma unroll
+    for (int q = 0; q < B_KO; q++) {
+      const long long gk = k0 + b_kk[q];
+      b_kok[q] = gk < p.K;
+      b_ko[q] = __ldg(p.offBk + (b_kok[q] ? gk : 0));
+    }
+#pragma unroll
+    for (int q = 0; q < A_KO; q++) {
+      const long long gk = k0 + a_kk[q];
+      a_kok[q] = gk < p.K;
+      a_ko[q] = __ldg(p.offAk + (a_kok[q] ? gk : 0));
+    }
+  };
+  auto issue_stage = [&](int stage) {
     const unsigned sbase = smem_base + (unsigned)(stage * STAGE_ELEMS) * 16u;
 #pragma unroll
-    for (int j = 0; j < B_EPT; j++) {
-      const long long gk = k0 + b_kk[j];
-      const bool ok = b_ok[j] && gk < p.K;
-      const long long ko = __ldg(p.offBk + (gk < p.K ? gk : 0));
-      cp_async16(sbase + (unsigned)b_slot[j] * 16u, p.B + (b_off[j] + ko), ok);
-    }
+    for (int q = 0; q < B_KO; q++)
 #pragma unroll
-    for (int j = 0; j < A_EPT; j++) {
-      const long long gk = k0 + a_kk[j];
-      const bool ok = a_ok[j] && gk < p.K;
-      const long long ko = __ldg(p.offAk + (gk < p.K ? gk : 0));
-      cp_async16(sbase + (unsigned)a_slot[j] * 16u, p.A + (a_off[j] + ko), ok);
-    }
+      for (int j = 0; j < B_ROWS; j++)
+        cp_async16(sbase + (unsigned)(b_rslot[j] + b_kslot[q]) * 16u, p.B + (b_off[j] + b_ko[q]), b_ok[j] && b_kok[q]);
+#pragma unroll
+    for (int q = 0; q < A_KO; q++)
+#pragma unroll
+      for (int j = 0; j < A_COLS; j++)
+        cp_async16(sbase + (unsigned)(a_cslot[j] + a_kslot[q]) * 16u, p.A + (a_off[j] + a_ko[q]), a_ok[j] && a_kok[q]);
   };
 
   double cr[TI][TJ][2], ci[TI][TJ][2];
@@ -252,39 +282,50 @@ k1_kernel(const __grid_constant__ K1Args p) {
   const int nk = (int)((p.K + BK - 1) / BK);
 #pragma unroll
   for (int s = 0; s < STAGES - 1; s++) {
-    if (s < nk) load_stage(s, (long long)s * BK);
+    if (s < nk) { fetch_ko((long long)s * BK); issue_stage(s); }
     cp_async_commit();
   }
+  if (STAGES - 1 < nk) fetch_ko((long long)(STAGES - 1) * BK); // offsets of the first in-loop stage
+
+  auto compute_kb = [&](const double2* sB, const double2* sA, int kb) {
+    double2 bf[TI], af[TJ];
+#pragma unroll
+    for (int i = 0; i < TI; i++) bf[i] = sB[((wn * TI + i) * (BK / 4) + kb) * 32 + lane];
+#pragma unroll
+    for (int j = 0; j < TJ; j++) af[j] = sA[(kb * (BM / 8) + wm * TJ + j) * 32 + lane];
+    // four passes so that the two DMMAs feeding one accumulator are TI*TJ*2 issues apart
+#pragma unroll
+    for (int i = 0; i < TI; i++)
+#pragma unroll
+      for (int j = 0; j < TJ; j++) {
+        dmma884(cr[i][j][0], cr[i][j][1], bf[i].x, af[j].x);
+        dmma884(ci[i][j][0], ci[i][j][1], bf[i].x, af[j].y);
+      }
+#pragma unroll
+    for (int i = 0; i < TI; i++)
+#pragma unroll
+      for (int j = 0; j < TJ; j++) {
+        dmma884(cr[i][j][0], cr[i][j][1], -bf[i].y, af[j].y); // SASS DMMA negates the operand for free
+        dmma884(ci[i][j][0], ci[i][j][1], bf[i].y, af[j].x);
+      }
+  };
 
   for (int kc = 0; kc < nk; kc++) {
     cp_async_wait<STAGES - 2>();
     __syncthreads();
-    {
-      const int nxt = kc + STAGES - 1;
-      if (nxt < nk) load_stage(nxt % STAGES, (long long)nxt * BK);
-      cp_async_commit();
-    }
     const double2* sB = smem + (kc % STAGES) * STAGE_ELEMS;
     const double2* sA = sB + BN * BK;
 #pragma unroll
-    for (int kb = 0; kb < BK / 4; kb++) {
-      double2 bf[TI], af[TJ];
-#pragma unroll
-      for (int i = 0; i < TI; i++) bf[i] = sB[((wn * TI + i) * (BK / 4) + kb) * 32 + lane];
-#pragma unroll
-      for (int j = 0; j < TJ; j++) af[j] = sA[(kb * (BM / 8) + wm * TJ + j) * 32 + lane];
-#pragma unroll
-      for (int i = 0; i < TI; i++) {
-        const double nbi = -bf[i].y;
-#pragma unroll
-        for (int j = 0; j < TJ; j++) {
-          dmma884(cr[i][j][0], cr[i][j][1], bf[i].x, af[j].x);
-          dmma884(ci[i][j][0], ci[i][j][1], bf[i].x, af[j].y);
-          dmma884(cr[i][j][0], cr[i][j][1], nbi, af[j].y);
-          dmma884(ci[i][j][0], ci[i][j][1], bf[i].y, af[j].x);
-        }
-      }
+    for (int kb = 0; kb < BK / 8; kb++) compute_kb(sB, sA, kb);
+    {
+      // stage (kc-1)%STAGES was fully consumed before this iteration's barrier
+      const int nxt = kc + STAGES - 1;
+      if (nxt < nk) issue_stage(nxt % STAGES);
+      cp_async_commit();
+      if (nxt + 1 < nk) fetch_ko((long long)(nxt + 1) * BK); // lands during the remaining DMMAs
     }
+#pragma unroll
+    for (int kb = BK / 8; kb < BK / 4; kb++) compute_kb(sB, sA, kb);
   }
   cp_async_wait<0>();
 
@@ -330,6 +371,7 @@ int ensure_tab(tncb_ctx* ctx, size_t elems) {
   size_t want = std::max(elems, (size_t)1 << 20);
   TNCB_CUDA(cudaMallocAsync((void**)&ctx->tab, want * sizeof(long long), ctx->stream));
   ctx->tab_elems = want;
+  ctx->tab_valid = false;
   return TNCB_OK;
 }
 
@@ -416,11 +458,17 @@ static int launch_k1(tncb_ctx* ctx, const PairPlan& P, const double2* A, const d
   const size_t tab_elems = (size_t)(P.M + P.N + 2 * P.K);
   int rc = ensure_tab(ctx, tab_elems);
   if (rc) return rc;
-  {
+  auto same = [](const LegList& x, const LegList& y) {
+    if (x.n != y.n) return false;
+    for (int i = 0; i < x.n; i++) if (x.dim[i] != y.dim[i] || x.sa[i] != y.sa[i] || x.sb[i] != y.sb[i]) return false;
+    return true;
+  };
+  if (!(ctx->tab_valid && same(ctx->tab_m, P.m) && same(ctx->tab_n, P.n) && same(ctx->tab_k, P.k))) {
     const long long total = (long long)tab_elems;
     const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)ctx->sm_count * 8);
     build_tables_kernel<<<blocks, 256, 0, ctx->stream>>>(P.m, P.n, P.k, P.M, P.N, P.K, ctx->tab);
     ctx->launches++;
+    ctx->tab_m = P.m; ctx->tab_n = P.n; ctx->tab_k = P.k; ctx->tab_valid = true;
   }
   K1Args a;
   a.A = A; a.B = B; a.C = C;

@@ -183,6 +183,20 @@ int tncb_tensor_download(tncb_ctx* ctx, const tncb_tensor* t, double* host) {
   return TNCB_OK;
 }
 
+int tncb_tensor_write(tncb_ctx* ctx, tncb_tensor* t, const double* host) {
+  if (!ctx || !t || !host) return fail(TNCB_ERR_INVALID, "null argument");
+  TNCB_CUDA(cudaSetDevice(ctx->device));
+  TNCB_CUDA(cudaMemcpyAsync(t->ptr, host, t->elems * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
+  return TNCB_OK;
+}
+
+int tncb_tensor_read(tncb_ctx* ctx, const tncb_tensor* t, double* host) {
+  if (!ctx || !t || !host) return fail(TNCB_ERR_INVALID, "null argument");
+  TNCB_CUDA(cudaSetDevice(ctx->device));
+  TNCB_CUDA(cudaMemcpyAsync(host, t->ptr, t->elems * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
+  return TNCB_OK;
+}
+
 int tncb_tensor_free(tncb_ctx* ctx, tncb_tensor* t) {
   if (!t) return TNCB_OK;
   if (!ctx) return fail(TNCB_ERR_INVALID, "ctx is null");
