@@ -104,6 +104,26 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def effective_cpus() -> int:
+    """Host cores this process may actually use: min(affinity, cgroup CPU quota).  The GPU boxes
+    expose 128 logical CPUs but cap the container at 16 (cpu.max = 1600000 100000); running MKL
+    with 128 threads there is 16x *slower* than with 16, so the baseline uses the quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(int(q) / int(per))))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, q // per))
+        except Exception:
+            pass
+    return n
+
+
 def cpu_pair_seconds(a_legs, a, b_legs, b, repeats):
     """The oracle's TTGT restatement with torch-CPU (MKL zgemm), all host threads."""
     import torch
@@ -125,7 +145,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = effective_cpus()
     torch.set_num_threads(cores)
     a_legs, a_dims, b_legs, b_dims = c2_problem()
     rng = np.random.default_rng(20240612)
@@ -250,13 +270,13 @@ def run_ours(args):
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
+            cores = effective_cpus()
             torch.set_num_threads(cores)
             cpu_pair_seconds(a_legs, a, b_legs, b, 1)
             ts = cpu_pair_seconds(a_legs, a, b_legs, b, 5)
             sec = float(np.mean(ts))
             cpu = {"value": 1.0 / sec, "unit": "contractions/s", "cores": cores, "kind": "port",
-                   "sample": "5 full C2 pairs after 1 warm-up (oracle TTGT: permute+contiguous+MKL zgemm via torch-CPU)",
+                   "sample": f"5 full C2 pairs after 1 warm-up (oracle TTGT: permute+contiguous+MKL zgemm via torch-CPU, {cores} threads = cgroup quota of {os.cpu_count()} logical CPUs)",
                    "zgemm_tflops": flops / sec * 1e-12, "ms_per_pair": sec * 1e3}
         ach = flops / (kern_ms * 1e-3) * 1e-12
         line = {

@@ -1,0 +1,84 @@
+"""Worker for the world_size>1 tests (spawned by tests/test_dist.py and by torchrun on the GPU box)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def build_case(qubits=10, rounds=6, seed=22, parts=2):
+    from tnc_b200.builders import random_circuit
+    from tnc_b200.contractionpath.paths import Cotengrust
+    from tnc_b200.tensornetwork.partitioning import find_partitioning, partition_tensor_network
+    tn = random_circuit(qubits, rounds, 0.5, 0.5, np.random.default_rng(seed))
+    part = find_partitioning(tn, parts, seed=1)
+    ptn = partition_tensor_network(tn, part)
+    opt = Cotengrust(ptn); opt.find_path()
+    flat = Cotengrust(tn); flat.find_path()
+    return tn, flat.get_best_replace_path(), ptn, opt.get_best_replace_path()
+
+
+def cpu_logic(rank, world, port, q):
+    """gloo, no GPU: metadata paths only (broadcast, mapping, scatter, fan-in schedule)."""
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tnc_b200.contractionpath import path
+        from tnc_b200.dist import broadcast_path, fanin_schedule, get_tensor_mapping, scatter_tensor_network
+        # integration_tests.rs:85-116 test_broadcast_contraction_path
+        ref = [(0, 1), (0, 2), (3, 4), (0, 3)]
+        got = broadcast_path(ref if rank == 0 else None, 0)
+        assert got == ref
+        tn, fpath, ptn, ppath = build_case(parts=world) if rank == 0 else (None, None, None, None)
+        local_tn, local_path, comm = scatter_tensor_network(ptn, ppath, rank, world)
+        toplevel = broadcast_path(ppath.toplevel if rank == 0 else None, 0)
+        mine = comm.tensor(rank)
+        assert mine is not None and local_tn.is_composite()
+        assert len(local_path.toplevel) == len(local_tn.tensors) - 1
+        ev = fanin_schedule(comm, toplevel)
+        assert len(ev) == world - 1 and ev[-1]["receiver"] == 0
+        assert ev[-1]["out_legs"] == []          # amplitude network: scalar at the end
+        summary = (sorted(comm.tensor_mapping.items()), [(e["sender"], e["receiver"], tuple(e["recv_dims"])) for e in ev],
+                   len(local_tn.tensors))
+        q.put((rank, summary))
+    finally:
+        dist.destroy_process_group()
+
+
+def gpu_main():
+    """torchrun entry on the GPU box: partitioned contraction over NCCL == flat contraction."""
+    import time
+    import torch
+    import torch.distributed as dist
+    import tnc_b200 as tb
+    from tnc_b200.dist import contract_partitioned, init_device_comm
+    from tnc_b200.tensornetwork import contract_tensor_network
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = tb.Context(local)
+    init_device_comm(ctx)
+    q, r = int(os.environ.get("TNCB_Q", "20")), int(os.environ.get("TNCB_R", "8"))
+    tn, fpath, ptn, ppath = build_case(q, r, 5, world) if rank == 0 else (None, None, None, None)
+    for it in range(3):
+        dist.barrier(); ctx.synchronize()
+        t0 = time.perf_counter()
+        res = contract_partitioned(ptn, ppath, ctx)
+        if rank == 0:
+            amp = complex(res.to_numpy())
+        ctx.synchronize(); dist.barrier()
+        dt = time.perf_counter() - t0
+    if rank == 0:
+        t0 = time.perf_counter(); flat = complex(contract_tensor_network(tn, fpath, ctx=ctx).to_numpy()); tf = time.perf_counter() - t0
+        err = abs(amp - flat)
+        print(f"DIST_OK world={world} q={q} r={r} partitioned={amp} flat={flat} abs_err={err:.3e} t_part={dt*1e3:.2f}ms t_flat={tf*1e3:.2f}ms", flush=True)
+        assert err <= 1e-9 * abs(flat) + 1e-14
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    gpu_main()

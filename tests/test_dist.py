@@ -1,0 +1,49 @@
+"""N>1 path.  CPU: world_size-2/3 gloo tests of the host-side logic (broadcast, mapping, scatter,
+fan-in schedule agree on all ranks) -- the counterpart of the reference's #[mpi_test]s
+(tnc/tests/integration_tests.rs:85-164).  GPU: NCCL fan-in == flat when >= 2 devices exist."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gloo_host_logic(built_lib, world):
+    import dist_worker
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = free_port()
+    procs = [ctx.Process(target=dist_worker.cpu_logic, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    res = dict(q.get(timeout=5) for _ in range(world))
+    assert len(res) == world
+    # mapping and fan-in schedule are identical on every rank
+    assert all(res[r][0] == res[0][0] and res[r][1] == res[0][1] for r in range(world))
+    assert sorted(r for _, r in res[0][0]) == list(range(world))
+
+
+@pytest.mark.gpu
+def test_nccl_fanin_equals_flat():
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    world = 2
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(free_port()), os.path.join(ROOT, "tests", "dist_worker.py")]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0 and "DIST_OK" in r.stdout, r.stdout[-3000:]

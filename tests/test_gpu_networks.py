@@ -1,0 +1,123 @@
+"""GPU tests for whole networks: random-circuit amplitude networks (the reference's benchmark
+inputs) against the oracle at sizes the oracle finishes in seconds, and size-independent
+properties at larger sizes: <0|U^dagger U|0> = 1, path independence, partitioned == flat
+(tnc/tests/integration_tests.rs:22-83)."""
+import numpy as np
+import pytest
+
+from oracle import tnc_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def to_oracle(t):
+    if t.is_composite():
+        return orc.OTensor(children=[to_oracle(c) for c in t.tensors])
+    td = t.tensordata
+    if td.kind == "gate":
+        d = ("gate", td.gate[0], td.gate[1], td.gate[2])
+    elif td.kind == "matrix":
+        d = np.asarray(td.matrix)
+    else:
+        d = None
+    return orc.OTensor(list(t.legs), list(t.bond_dims), d)
+
+
+def to_opath(p):
+    return orc.OPath(list(p.toplevel), {i: to_opath(q) for i, q in p.nested.items()})
+
+
+def greedy(tn):
+    from tnc_b200.contractionpath.paths import Cotengrust
+    opt = Cotengrust(tn)
+    opt.find_path()
+    return opt.get_best_replace_path()
+
+
+@pytest.mark.parametrize("qubits,rounds,seed", [(8, 6, 1), (12, 8, 2), (16, 8, 3), (20, 8, 4)])
+def test_random_circuit_amplitude_vs_oracle(ctx, qubits, rounds, seed):
+    from tnc_b200.builders import random_circuit
+    from tnc_b200.tensornetwork import contract_tensor_network
+    tn = random_circuit(qubits, rounds, 0.5, 0.5, np.random.default_rng(seed))
+    path = greedy(tn)
+    res = contract_tensor_network(tn, path, ctx=ctx)
+    ref = orc.contract_tensor_network(to_oracle(tn), to_opath(path))
+    assert res.legs == ref.legs == []
+    got, exp = complex(res.to_numpy()), complex(ref.data)
+    assert abs(got - exp) <= 1e-9 * max(abs(exp), 1e-300) + 1e-18, (got, exp)  # rel 1e-9 on amplitudes
+
+
+def test_statevector_vs_oracle(ctx):
+    from tnc_b200.builders import random_circuit_builder
+    from tnc_b200.tensornetwork import contract_tensor_network
+    c = random_circuit_builder(10, 6, 0.5, 0.5, np.random.default_rng(5))
+    tn, perm = c.into_statevector_network()
+    path = greedy(tn)
+    res = perm.apply(contract_tensor_network(tn, path, ctx=ctx), ctx=ctx)
+    ref = orc.permute_to(orc.contract_tensor_network(to_oracle(tn), to_opath(path)), perm.target_leg_order)
+    sv = res.to_numpy()
+    assert np.abs(sv - ref.data).max() <= 1e-12
+    assert abs(np.vdot(sv, sv) - 1) < 1e-12  # unitary circuit
+
+
+def echo_circuit(qubits, rounds, seed):
+    """U followed by U^dagger (adjoint gates in reverse order)."""
+    from tnc_b200.builders import Circuit, random_circuit_builder
+    c = random_circuit_builder(qubits, rounds, 0.5, 0.5, np.random.default_rng(seed))
+    gates = [(t.tensordata.gate, None) for t in c.tensors if t.tensordata.kind == "gate"]
+    # recover qubit indices by replaying the leg bookkeeping
+    c2 = Circuit(); q = c2.allocate_register(qubits)
+    log = []
+    edge_owner = {e: i for i, e in enumerate(c2.open_edges)}
+    for t in c.tensors:
+        if t.tensordata.kind != "gate":
+            continue
+        k = len(t.legs) // 2
+        qs = [edge_owner[e] for e in t.legs[:k]]
+        for qq, e in zip(qs, t.legs[k:]):
+            edge_owner[e] = qq
+        name, angles, adj = t.tensordata.gate
+        c2.append_gate(name, angles, qs, adjoint=adj)
+        log.append((name, angles, qs, adj))
+    for name, angles, qs, adj in reversed(log):
+        c2.append_gate(name, angles, qs, adjoint=not adj)
+    return c2
+
+
+@pytest.mark.parametrize("qubits,rounds", [(12, 6), (16, 6), (20, 5)])
+def test_echo_amplitude_is_one(ctx, qubits, rounds):
+    from tnc_b200.tensornetwork import contract_tensor_network
+    tn, _ = echo_circuit(qubits, rounds, 11).into_amplitude_network("0" * qubits)
+    res = contract_tensor_network(tn, greedy(tn), ctx=ctx)
+    assert abs(complex(res.to_numpy()) - 1.0) <= 1e-10
+
+
+def test_partitioned_equals_flat(ctx):
+    from tnc_b200.builders import random_circuit
+    from tnc_b200.tensornetwork import Tensor, contract_tensor_network
+    tn = random_circuit(10, 6, 0.5, 0.5, np.random.default_rng(22))
+    flat = complex(contract_tensor_network(tn, greedy(tn), ctx=ctx).to_numpy())
+    for parts in (2, 4, 7):
+        n = len(tn.tensors)
+        groups = [tn.tensors[i * n // parts:(i + 1) * n // parts] for i in range(parts)]
+        ptn = Tensor.new_composite([Tensor.new_composite(g) for g in groups])
+        path = greedy(ptn)
+        assert set(path.nested) == set(range(parts))
+        got = complex(contract_tensor_network(ptn, path, ctx=ctx).to_numpy())
+        assert abs(got - flat) <= 1e-9 * abs(flat) + 1e-14  # amplitudes can be exactly 0
+
+
+def test_path_independence(ctx):
+    from tnc_b200.builders import random_circuit
+    from tnc_b200.contractionpath import ContractionPath
+    from tnc_b200.tensornetwork import contract_tensor_network
+    tn = random_circuit(10, 6, 0.5, 0.5, np.random.default_rng(31))
+    a = complex(contract_tensor_network(tn, greedy(tn), ctx=ctx).to_numpy())
+    # a second valid path: greedy on the reversed tensor list, mapped back
+    n = len(tn.tensors)
+    from tnc_b200.tensornetwork import Tensor
+    rev = Tensor.new_composite(list(reversed(tn.tensors)))
+    p = greedy(rev)
+    mapped = ContractionPath.simple([(n - 1 - i, n - 1 - j) for i, j in p.toplevel])
+    b = complex(contract_tensor_network(tn, mapped, ctx=ctx).to_numpy())
+    assert abs(a - b) <= 1e-10 * abs(a) + 1e-18

@@ -1,3 +1,5 @@
 from .circuit_builder import Circuit, Permutor
+from .random_circuit import random_circuit, random_circuit_builder
+from .sycamore_circuit import sycamore_circuit
 
-__all__ = ["Circuit", "Permutor"]
+__all__ = ["Circuit", "Permutor", "random_circuit", "random_circuit_builder", "sycamore_circuit"]

@@ -155,6 +155,8 @@ struct K1Args {
   const long long* offBk;
   long long M, N, K;
   int tiles_m, tiles_n;
+  int ksplit;           // >1: blockIdx.x / tiles selects a K range, C points at the partial buffer
+  int chunks_per_split; // BK-chunks per K range
 };
 
 // Shared-memory tiles are stored in DMMA fragment order so that every fragment load is one
@@ -198,9 +200,11 @@ k1_kernel(const __grid_constant__ K1Args p) {
 
   // grouped rasterisation: 8 n-tiles share the same band of At columns in L2
   int tn, tm;
+  const int n_tiles = p.tiles_m * p.tiles_n;
+  const int split = blockIdx.x / n_tiles;
   {
     const int GROUP = 8;
-    const int t = blockIdx.x;
+    const int t = blockIdx.x - split * n_tiles;
     const int per_group = GROUP * p.tiles_m;
     const int gid = t / per_group;
     const int first_n = gid * GROUP;
@@ -279,13 +283,16 @@ k1_kernel(const __grid_constant__ K1Args p) {
 #pragma unroll
     for (int j = 0; j < TJ; j++) { cr[i][j][0] = cr[i][j][1] = 0.0; ci[i][j][0] = ci[i][j][1] = 0.0; }
 
-  const int nk = (int)((p.K + BK - 1) / BK);
+  const int nk_total = (int)((p.K + BK - 1) / BK);
+  const int kc_begin = split * p.chunks_per_split;
+  const int nk = max(0, min(nk_total - kc_begin, p.chunks_per_split));
+  const long long kbase = (long long)kc_begin * BK;
 #pragma unroll
   for (int s = 0; s < STAGES - 1; s++) {
-    if (s < nk) { fetch_ko((long long)s * BK); issue_stage(s); }
+    if (s < nk) { fetch_ko(kbase + (long long)s * BK); issue_stage(s); }
     cp_async_commit();
   }
-  if (STAGES - 1 < nk) fetch_ko((long long)(STAGES - 1) * BK); // offsets of the first in-loop stage
+  if (STAGES - 1 < nk) fetch_ko(kbase + (long long)(STAGES - 1) * BK); // offsets of the first in-loop stage
 
   auto compute_kb = [&](const double2* sB, const double2* sA, int kb) {
     double2 bf[TI], af[TJ];
@@ -322,7 +329,7 @@ k1_kernel(const __grid_constant__ K1Args p) {
       const int nxt = kc + STAGES - 1;
       if (nxt < nk) issue_stage(nxt % STAGES);
       cp_async_commit();
-      if (nxt + 1 < nk) fetch_ko((long long)(nxt + 1) * BK); // lands during the remaining DMMAs
+      if (nxt + 1 < nk) fetch_ko(kbase + (long long)(nxt + 1) * BK); // lands during the remaining DMMAs
     }
 #pragma unroll
     for (int kb = BK / 8; kb < BK / 4; kb++) compute_kb(sB, sA, kb);
@@ -338,7 +345,7 @@ k1_kernel(const __grid_constant__ K1Args p) {
 #pragma unroll
     for (int j = 0; j < TJ; j++) {
       const long long gm = m0 + (wm * TJ + j) * 8 + t2;
-      double2* dst = p.C + gn * p.M + gm;
+      double2* dst = p.C + (long long)split * p.M * p.N + gn * p.M + gm;
       if (gm < p.M) dst[0] = make_double2(cr[i][j][0], ci[i][j][0]);
       if (gm + 1 < p.M) dst[1] = make_double2(cr[i][j][1], ci[i][j][1]);
     }
@@ -436,7 +443,7 @@ static int launch_k1_cfg(tncb_ctx* ctx, const K1Args& a) {
   auto kern = k1_kernel<BN, BM, WN, WM, ST, BKF, AKF>;
   const size_t smem = (size_t)ST * (BN * K1_BK + K1_BK * BM) * sizeof(double2);
   TNCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const long long tiles = (long long)a.tiles_m * a.tiles_n;
+  const long long tiles = (long long)a.tiles_m * a.tiles_n * a.ksplit;
   if (tiles > 0x7fffffffLL) return fail(TNCB_ERR_UNSUPPORTED, "K1 grid too large");
   kern<<<(unsigned)tiles, WN * WM * 32, smem, ctx->stream>>>(a);
   ctx->launches++;
@@ -445,13 +452,42 @@ static int launch_k1_cfg(tncb_ctx* ctx, const K1Args& a) {
 }
 
 template <int BN, int BM, int WN, int WM, int ST>
-static int launch_k1_modes(tncb_ctx* ctx, K1Args& a, bool bkf, bool akf) {
+static int launch_k1_modes(tncb_ctx* ctx, K1Args& a, bool bkf, bool akf, bool allow_split) {
   a.tiles_m = (int)((a.M + BM - 1) / BM);
   a.tiles_n = (int)((a.N + BN - 1) / BN);
-  if (bkf && akf) return launch_k1_cfg<BN, BM, WN, WM, ST, true, true>(ctx, a);
-  if (bkf && !akf) return launch_k1_cfg<BN, BM, WN, WM, ST, true, false>(ctx, a);
-  if (!bkf && akf) return launch_k1_cfg<BN, BM, WN, WM, ST, false, true>(ctx, a);
-  return launch_k1_cfg<BN, BM, WN, WM, ST, false, false>(ctx, a);
+  // split-K: few output tiles but a long K would leave most SMs idle (C4: M=2^8, N=2^6, K=2^20
+  // ran on 4 CTAs at 0.67 TFLOP/s).  Each K range writes its own partial C, reduced in a
+  // fixed order afterwards (deterministic, no atomics).
+  const long long tiles = (long long)a.tiles_m * a.tiles_n;
+  const int nk_total = (int)((a.K + K1_BK - 1) / K1_BK);
+  double2* final_c = a.C;
+  a.ksplit = 1; a.chunks_per_split = nk_total;
+  const long long want_ctas = 2LL * ctx->sm_count;
+  if (allow_split && tiles < want_ctas && nk_total >= 16) {
+    long long ks = std::min<long long>((want_ctas + tiles - 1) / tiles, nk_total / 8);
+    const long long ws_cap = ((long long)1 << 30) / 16 / std::max(1LL, a.M * a.N); // <= 1 GiB of partials
+    ks = std::max(1LL, std::min(ks, ws_cap));
+    if (ks > 1) {
+      a.chunks_per_split = (int)((nk_total + ks - 1) / ks);
+      a.ksplit = (nk_total + a.chunks_per_split - 1) / a.chunks_per_split;
+      int rc = ensure_partial(ctx, (size_t)(a.M * a.N * a.ksplit));
+      if (rc) return rc;
+      a.C = ctx->partial;
+    }
+  }
+  int rc;
+  if (bkf && akf) rc = launch_k1_cfg<BN, BM, WN, WM, ST, true, true>(ctx, a);
+  else if (bkf && !akf) rc = launch_k1_cfg<BN, BM, WN, WM, ST, true, false>(ctx, a);
+  else if (!bkf && akf) rc = launch_k1_cfg<BN, BM, WN, WM, ST, false, true>(ctx, a);
+  else rc = launch_k1_cfg<BN, BM, WN, WM, ST, false, false>(ctx, a);
+  if (rc) return rc;
+  if (a.ksplit > 1) {
+    const long long MN = a.M * a.N;
+    reduce_partials_kernel<<<(unsigned)((MN + 255) / 256), 256, 0, ctx->stream>>>(ctx->partial, final_c, MN, a.ksplit);
+    ctx->launches++;
+    TNCB_CUDA(cudaGetLastError());
+  }
+  return TNCB_OK;
 }
 
 static int launch_k1(tncb_ctx* ctx, const PairPlan& P, const double2* A, const double2* B, double2* C) {
@@ -476,8 +512,8 @@ static int launch_k1(tncb_ctx* ctx, const PairPlan& P, const double2* A, const d
   a.M = P.M; a.N = P.N; a.K = P.K;
   const long long big_tiles = ((P.M + 63) / 64) * ((P.N + 127) / 128);
   if (big_tiles >= 2LL * ctx->sm_count)
-    return launch_k1_modes<128, 64, 4, 2, 3>(ctx, a, P.b_kfast, P.a_kfast);
-  return launch_k1_modes<64, 64, 2, 2, 3>(ctx, a, P.b_kfast, P.a_kfast);
+    return launch_k1_modes<128, 64, 4, 2, 3>(ctx, a, P.b_kfast, P.a_kfast, false);
+  return launch_k1_modes<64, 64, 2, 2, 3>(ctx, a, P.b_kfast, P.a_kfast, true);
 }
 
 int launch_pair(tncb_ctx* ctx, const PairPlan& P, const double2* A, const double2* B, double2* C) {

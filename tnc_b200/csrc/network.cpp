@@ -10,6 +10,8 @@
 #include "internal.h"
 #include <algorithm>
 #include <complex>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace tncb {
@@ -197,6 +199,11 @@ static int execute(tncb_ctx* ctx, const Schedule& S, const tncb_tn* tn, tncb_ten
     else live[s].ptr = (double2*)leaf_block + S.leaf_offset[li];
   }
   int rc = TNCB_OK;
+  // TNCB_TRACE=1: per-step device times on stderr (tuning aid; adds two events per pair)
+  const bool trace = std::getenv("TNCB_TRACE") != nullptr;
+  std::vector<cudaEvent_t> tev;
+  if (trace) { tev.resize(S.steps.size() + 1); for (auto& e : tev) cudaEventCreate(&e); cudaEventRecord(tev[0], ctx->stream); }
+  size_t step_no = 0;
   for (const Step& st : S.steps) {
     const SlotMeta& om = S.slots[st.out];
     size_t bytes = std::max<size_t>(om.elems * sizeof(double2), 16);
@@ -209,6 +216,18 @@ static int execute(tncb_ctx* ctx, const Schedule& S, const tncb_tn* tn, tncb_ten
       else if (live[s].bytes) ctx->arena.free(live[s].ptr, live[s].bytes);
       live[s].ptr = nullptr; live[s].bytes = 0;
     }
+    if (trace) cudaEventRecord(tev[++step_no], ctx->stream);
+  }
+  if (trace) {
+    cudaStreamSynchronize(ctx->stream);
+    for (size_t q = 0; q < step_no; q++) {
+      float ms = 0; cudaEventElapsedTime(&ms, tev[q], tev[q + 1]);
+      const PairPlan& P = S.steps[q].plan;
+      fprintf(stderr, "TNCB_TRACE step %zu class K%d M %lld N %lld K %lld groups m%d n%d k%d akf %d bkf %d ms %.4f tflops %.2f gbs %.1f\n",
+              q, P.kernel_class, P.M, P.N, P.K, P.m.n, P.n.n, P.k.n, (int)P.a_kfast, (int)P.b_kfast, ms,
+              P.flops() / (ms * 1e-3) * 1e-12, P.bytes() / (ms * 1e-3) * 1e-9);
+    }
+    for (auto& e : tev) cudaEventDestroy(e);
   }
   tncb_tensor* result = nullptr;
   if (!rc && S.result_slot >= 0) {
