@@ -41,6 +41,10 @@ def cpu_logic(rank, world, port, q):
         ev = fanin_schedule(comm, toplevel)
         assert len(ev) == world - 1 and ev[-1]["receiver"] == 0
         assert ev[-1]["out_legs"] == []          # amplitude network: scalar at the end
+        # the broadcast leg orders are the true orders of the contracted partitions
+        from tnc_b200.dist.communication import contracted_legs
+        assert comm.external[mine] == contracted_legs(local_tn, local_path)
+        assert sorted(comm.external[mine][0]) == sorted(local_tn.external_tensor().legs)
         summary = (sorted(comm.tensor_mapping.items()), [(e["sender"], e["receiver"], tuple(e["recv_dims"])) for e in ev],
                    len(local_tn.tensors))
         q.put((rank, summary))
@@ -81,4 +85,10 @@ def gpu_main():
 
 
 if __name__ == "__main__":
-    gpu_main()
+    try:
+        gpu_main()
+    except BaseException:  # fail fast: never leave the other ranks waiting in a collective
+        import traceback
+        traceback.print_exc()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(1)

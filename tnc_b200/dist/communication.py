@@ -77,6 +77,27 @@ class Communication:
         return None
 
 
+def contracted_legs(tn: Tensor, path: ContractionPath) -> Tuple[List[int], List[int]]:
+    """Leg order of `contract_tensor_network(tn, path)` from metadata alone: replay
+    `b ^ a` (contraction.rs:64) along the path.  The reference does not need this because the
+    serialised tensor carries its legs (serialization.rs:43-67); here only raw data travels."""
+    if tn.is_leaf():
+        return list(tn.legs), list(tn.bond_dims)
+    ts: List[Optional[Tensor]] = []
+    for i, c in enumerate(tn.tensors):
+        if c.is_composite() and i in path.nested:
+            l, d = contracted_legs(c, path.nested[i])
+            ts.append(Tensor(l, d))
+        else:
+            ts.append(Tensor(c.legs, c.bond_dims) if c.is_leaf() else None)
+    for (i, j) in path.toplevel:
+        ts[i] = ts[j] ^ ts[i]
+        ts[j] = None
+    rest = [t for t in ts if t is not None]
+    assert len(rest) == 1, "Not fully contracted"
+    return list(rest[0].legs), list(rest[0].bond_dims)
+
+
 def fanin_schedule(comm: Communication, toplevel) -> List[dict]:
     """The fan-in as a list of events every rank derives identically from metadata:
     {receiver, sender, recv_legs, recv_dims, out_legs, out_dims} per top-level pair."""
@@ -116,8 +137,8 @@ def scatter_tensor_network(r_tn: Optional[Tensor], path: Optional[ContractionPat
         mapping = get_tensor_mapping(path, size)
         external = {}
         for p in mapping:
-            e = r_tn.tensor(p).external_tensor()
-            external[p] = (list(e.legs), list(e.bond_dims))
+            # true leg order of the contracted partition (depends on its local path)
+            external[p] = contracted_legs(r_tn.tensor(p), path.nested[p])
         comm = Communication(mapping, external)
         per_rank = [None] * size
         for p, r in mapping.items():
@@ -183,4 +204,6 @@ def contract_partitioned(r_tn: Optional[Tensor], path: Optional[ContractionPath]
     local_tn, local_path, comm = scatter_tensor_network(r_tn, path, rank, size, group)
     if local_tn.is_composite():
         local_tn = contract_tensor_network(local_tn, local_path, ctx=ctx)
+        mine = comm.tensor(rank)
+        assert local_tn.legs == comm.external[mine][0], "fan-in metadata out of sync with the device result"
     return intermediate_reduce_tensor_network(local_tn, toplevel, rank, comm, ctx)
