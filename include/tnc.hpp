@@ -1,0 +1,174 @@
+// tnc.hpp -- header-only C++ host-side mirror of the reference's interface for the hot path,
+// written above the C ABI of include/tncb.h (the Rust toolchain is absent in this image, the
+// reference is compiled code, so the compiled host side is C++).
+//
+//   tnc::Tensor            <- tnc::tensornetwork::tensor::Tensor        (tensor.rs:21-37)
+//   tnc::TensorData        <- tnc::tensornetwork::tensordata::TensorData (tensordata.rs:15-26)
+//   tnc::ContractionPath   <- tnc::contractionpath::ContractionPath     (contractionpath.rs:29-35)
+//   tnc::contract_tensor_network(Tensor, const ContractionPath&) -> Tensor   (contraction.rs:30)
+//
+// Errors: the reference panics; here every non-zero tncb_status becomes a tnc::Error exception.
+#pragma once
+#include <complex>
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "tncb.h"
+
+namespace tnc {
+
+using Complex64 = std::complex<double>;
+
+struct Error : std::runtime_error {
+  int status;
+  Error(int s, const std::string& m) : std::runtime_error(m), status(s) {}
+};
+inline void check(int rc) {
+  if (rc != TNCB_OK) {
+    std::string m = tncb_last_error();
+    throw Error(rc, m.empty() ? tncb_strerror(rc) : m);
+  }
+}
+
+class Context {
+ public:
+  explicit Context(int device = 0, size_t arena_bytes = 0) { check(tncb_ctx_create(device, arena_bytes, &h_)); }
+  ~Context() { tncb_ctx_destroy(h_); }
+  Context(const Context&) = delete;
+  Context& operator=(const Context&) = delete;
+  tncb_ctx* get() const { return h_; }
+ private:
+  tncb_ctx* h_ = nullptr;
+};
+
+// Device payload with shared ownership ("clone does not clone the data", like tetra::Tensor).
+struct DeviceData {
+  tncb_ctx* ctx = nullptr;
+  tncb_tensor* t = nullptr;
+  ~DeviceData() { if (t) tncb_tensor_free(ctx, t); }
+};
+
+struct TensorData {
+  enum Kind { Uncontracted, Gate, Matrix, Device } kind = Uncontracted;
+  std::string gate_name; std::vector<double> angles; bool adjoint = false;   // Gate((name, angles, adjoint))
+  std::vector<Complex64> matrix;                                             // Matrix (host, row-major)
+  std::shared_ptr<DeviceData> device;                                        // Matrix resident on the GPU
+
+  static TensorData gate(std::string name, std::vector<double> ang = {}, bool adj = false) {
+    TensorData d; d.kind = Gate; d.gate_name = std::move(name); d.angles = std::move(ang); d.adjoint = adj; return d;
+  }
+  // TensorData::new_from_data(dimensions, data, None)  (tensordata.rs:31-37)
+  static TensorData new_from_data(const std::vector<uint64_t>&, std::vector<Complex64> data) {
+    TensorData d; d.kind = Matrix; d.matrix = std::move(data); return d;
+  }
+};
+
+struct Tensor {
+  std::vector<Tensor> tensors;
+  std::vector<uint64_t> legs, bond_dims;
+  TensorData tensordata;
+
+  Tensor() = default;
+  Tensor(std::vector<uint64_t> l, std::vector<uint64_t> d) : legs(std::move(l)), bond_dims(std::move(d)) {}
+  static Tensor new_from_const(std::vector<uint64_t> l, uint64_t dim) {
+    std::vector<uint64_t> d(l.size(), dim); return Tensor(std::move(l), std::move(d));
+  }
+  static Tensor new_composite(std::vector<Tensor> ts) { Tensor t; t.tensors = std::move(ts); return t; }
+  bool is_leaf() const { return tensors.empty(); }
+  bool is_composite() const { return !tensors.empty(); }
+  void set_tensor_data(TensorData d) { tensordata = std::move(d); }
+  const Tensor& tensor(size_t i) const { return tensors.at(i); }
+
+  // `elements()`: row-major data of a contracted leaf (downloads from the device)
+  std::vector<Complex64> elements() const {
+    if (tensordata.kind == TensorData::Matrix) return tensordata.matrix;
+    if (tensordata.kind != TensorData::Device) throw Error(TNCB_ERR_UNCONTRACTED, "Cannot convert uncontracted tensor to data");
+    std::vector<Complex64> out(tncb_tensor_elements(tensordata.device->t));
+    check(tncb_tensor_download(tensordata.device->ctx, tensordata.device->t, reinterpret_cast<double*>(out.data())));
+    return out;
+  }
+};
+
+struct ContractionPath {
+  std::map<size_t, ContractionPath> nested;
+  std::vector<std::pair<size_t, size_t>> toplevel;
+  static ContractionPath simple(std::vector<std::pair<size_t, size_t>> p) { ContractionPath c; c.toplevel = std::move(p); return c; }
+  static ContractionPath single(size_t a, size_t b) { return simple({{a, b}}); }
+};
+
+namespace detail {
+struct Marshal {  // owns every buffer the C structs point into
+  std::vector<std::unique_ptr<std::vector<tncb_tn>>> tn_arrays;
+  std::vector<std::unique_ptr<std::vector<tncb_path>>> path_arrays;
+  std::vector<std::unique_ptr<std::vector<uint64_t>>> u64s;
+
+  tncb_tn tn(const Tensor& t) {
+    tncb_tn n{};
+    if (t.is_composite()) {
+      auto arr = std::make_unique<std::vector<tncb_tn>>();
+      for (const Tensor& c : t.tensors) arr->push_back(tn(c));
+      n.n_children = arr->size(); n.children = arr->data();
+      tn_arrays.push_back(std::move(arr));
+      return n;
+    }
+    n.rank = (int)t.legs.size(); n.legs = t.legs.data(); n.dims = t.bond_dims.data();
+    switch (t.tensordata.kind) {
+      case TensorData::Gate:
+        n.kind = TNCB_DATA_GATE; n.gate_name = t.tensordata.gate_name.c_str();
+        n.gate_angles = t.tensordata.angles.data(); n.n_gate_angles = (int)t.tensordata.angles.size();
+        n.gate_adjoint = t.tensordata.adjoint; break;
+      case TensorData::Matrix:
+        n.kind = TNCB_DATA_MATRIX; n.host_re_im = reinterpret_cast<const double*>(t.tensordata.matrix.data()); break;
+      case TensorData::Device:
+        n.kind = TNCB_DATA_DEVICE; n.device = t.tensordata.device->t; break;
+      default: n.kind = TNCB_DATA_UNCONTRACTED;
+    }
+    return n;
+  }
+  tncb_path path(const ContractionPath& p) {
+    tncb_path o{};
+    auto pairs = std::make_unique<std::vector<uint64_t>>();
+    for (auto& q : p.toplevel) { pairs->push_back(q.first); pairs->push_back(q.second); }
+    o.n_pairs = p.toplevel.size(); o.pairs = pairs->data();
+    u64s.push_back(std::move(pairs));
+    if (!p.nested.empty()) {
+      auto idx = std::make_unique<std::vector<uint64_t>>();
+      auto arr = std::make_unique<std::vector<tncb_path>>();
+      for (auto& kv : p.nested) { idx->push_back(kv.first); arr->push_back(path(kv.second)); }
+      o.n_nested = idx->size(); o.nested_index = idx->data(); o.nested = arr->data();
+      u64s.push_back(std::move(idx)); path_arrays.push_back(std::move(arr));
+    }
+    return o;
+  }
+};
+inline void release_device_inputs(Tensor& t) {  // the call consumed them (mem::take)
+  if (t.is_composite()) { for (Tensor& c : t.tensors) release_device_inputs(c); return; }
+  if (t.tensordata.kind == TensorData::Device && t.tensordata.device) t.tensordata.device->t = nullptr;
+}
+}  // namespace detail
+
+// Fully contracts `tn` (moved in, as in the reference) with the replace-left `path`.
+inline Tensor contract_tensor_network(Context& ctx, Tensor tn, const ContractionPath& path) {
+  detail::Marshal m;
+  tncb_tn c_tn = m.tn(tn);
+  tncb_path c_path = m.path(path);
+  tncb_tensor* out = nullptr; int n_out = 0; uint64_t legs[64];
+  check(tncb_contract_tensor_network(ctx.get(), &c_tn, &c_path, &out, &n_out, legs));
+  detail::release_device_inputs(tn);
+  Tensor res;
+  if (!out) return res;
+  res.legs.assign(legs, legs + n_out);
+  res.bond_dims.resize(n_out);
+  if (n_out) check(tncb_tensor_dims(out, res.bond_dims.data()));
+  res.tensordata.kind = TensorData::Device;
+  res.tensordata.device = std::make_shared<DeviceData>();
+  res.tensordata.device->ctx = ctx.get(); res.tensordata.device->t = out;
+  return res;
+}
+
+}  // namespace tnc

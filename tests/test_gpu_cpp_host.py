@@ -1,0 +1,17 @@
+"""Runs the C++ host-API test program (include/tnc.hpp over the C ABI) on the GPU box."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cpp_host_binary_builds(built_lib):
+    assert os.path.exists(os.path.join(ROOT, "build", "test_host_api"))
+
+
+@pytest.mark.gpu
+def test_cpp_host_api(built_lib):
+    r = subprocess.run([os.path.join(ROOT, "build", "test_host_api")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    assert r.returncode == 0 and "HOST_API_OK" in r.stdout, r.stdout
