@@ -16,6 +16,7 @@
 #include "internal.h"
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 namespace tncb {
 
@@ -133,6 +134,13 @@ __device__ __forceinline__ void cp_async16(unsigned smem_addr, const void* gptr,
   const int src = pred ? 16 : 0;
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_addr), "l"(gptr), "r"(src));
 }
+// volatile so that ptxas keeps the load where it is written (it otherwise sinks the prefetch to
+// its first use and the latency reappears as a long_scoreboard stall in the gather issue)
+__device__ __forceinline__ long long ldg_pinned(const long long* p) {
+  long long v;
+  asm volatile("ld.global.nc.s64 %0, [%1];\n" : "=l"(v) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N_>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N_)); }
@@ -172,8 +180,8 @@ struct K1Args {
 // prefetched one chunk ahead into registers and the cp.async gathers of stage kc+STAGES-1 are
 // issued in the middle of chunk kc's DMMA stream, so no table load sits on the critical path
 // (ncu r01: 20 % long_scoreboard on exactly those loads before this change).
-template <int BN, int BM, int WARPS_N, int WARPS_M, int STAGES, bool B_KFAST, bool A_KFAST>
-__global__ void __launch_bounds__(WARPS_N* WARPS_M * 32)
+template <int BN, int BM, int WARPS_N, int WARPS_M, int STAGES, bool B_KFAST, bool A_KFAST, int MINB = 1>
+__global__ void __launch_bounds__(WARPS_N* WARPS_M * 32, MINB)
 k1_kernel(const __grid_constant__ K1Args p) {
   constexpr int BK = K1_BK;
   constexpr int NW = WARPS_N * WARPS_M;
@@ -438,9 +446,9 @@ static int launch_k0(tncb_ctx* ctx, const PairPlan& P, const double2* A, const d
   return TNCB_OK;
 }
 
-template <int BN, int BM, int WN, int WM, int ST, bool BKF, bool AKF>
+template <int BN, int BM, int WN, int WM, int ST, bool BKF, bool AKF, int MINB = 1>
 static int launch_k1_cfg(tncb_ctx* ctx, const K1Args& a) {
-  auto kern = k1_kernel<BN, BM, WN, WM, ST, BKF, AKF>;
+  auto kern = k1_kernel<BN, BM, WN, WM, ST, BKF, AKF, MINB>;
   const size_t smem = (size_t)ST * (BN * K1_BK + K1_BK * BM) * sizeof(double2);
   TNCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long tiles = (long long)a.tiles_m * a.tiles_n * a.ksplit;
@@ -451,7 +459,7 @@ static int launch_k1_cfg(tncb_ctx* ctx, const K1Args& a) {
   return TNCB_OK;
 }
 
-template <int BN, int BM, int WN, int WM, int ST>
+template <int BN, int BM, int WN, int WM, int ST, int MINB = 1>
 static int launch_k1_modes(tncb_ctx* ctx, K1Args& a, bool bkf, bool akf, bool allow_split) {
   a.tiles_m = (int)((a.M + BM - 1) / BM);
   a.tiles_n = (int)((a.N + BN - 1) / BN);
@@ -476,10 +484,10 @@ static int launch_k1_modes(tncb_ctx* ctx, K1Args& a, bool bkf, bool akf, bool al
     }
   }
   int rc;
-  if (bkf && akf) rc = launch_k1_cfg<BN, BM, WN, WM, ST, true, true>(ctx, a);
-  else if (bkf && !akf) rc = launch_k1_cfg<BN, BM, WN, WM, ST, true, false>(ctx, a);
-  else if (!bkf && akf) rc = launch_k1_cfg<BN, BM, WN, WM, ST, false, true>(ctx, a);
-  else rc = launch_k1_cfg<BN, BM, WN, WM, ST, false, false>(ctx, a);
+  if (bkf && akf) rc = launch_k1_cfg<BN, BM, WN, WM, ST, true, true, MINB>(ctx, a);
+  else if (bkf && !akf) rc = launch_k1_cfg<BN, BM, WN, WM, ST, true, false, MINB>(ctx, a);
+  else if (!bkf && akf) rc = launch_k1_cfg<BN, BM, WN, WM, ST, false, true, MINB>(ctx, a);
+  else rc = launch_k1_cfg<BN, BM, WN, WM, ST, false, false, MINB>(ctx, a);
   if (rc) return rc;
   if (a.ksplit > 1) {
     const long long MN = a.M * a.N;
@@ -510,10 +518,15 @@ static int launch_k1(tncb_ctx* ctx, const PairPlan& P, const double2* A, const d
   a.A = A; a.B = B; a.C = C;
   a.offAm = ctx->tab; a.offBn = ctx->tab + P.M; a.offAk = ctx->tab + P.M + P.N; a.offBk = a.offAk + P.K;
   a.M = P.M; a.N = P.N; a.K = P.K;
-  const long long big_tiles = ((P.M + 63) / 64) * ((P.N + 127) / 128);
-  if (big_tiles >= 2LL * ctx->sm_count)
-    return launch_k1_modes<128, 64, 4, 2, 3>(ctx, a, P.b_kfast, P.a_kfast, false);
-  return launch_k1_modes<64, 64, 2, 2, 3>(ctx, a, P.b_kfast, P.a_kfast, true);
+  // Tile choice (A/B-measured on B200, C2 pair, profiles/r01_k1_tile_ab.txt): 64x64 tiles with a
+  // 2-stage ring and 2 co-resident CTAs per SM reach ~90 % of the DMMA peak (independent CTAs
+  // hide each other's per-chunk barrier/gather bubbles); 128x64 with 3-4 stages and 1 CTA/SM
+  // stays at 75-81 %.  Skinny outputs use a 32-wide tile on the narrow side.
+  static const int variant = std::getenv("TNCB_K1_VARIANT") ? atoi(std::getenv("TNCB_K1_VARIANT")) : 0;
+  if (variant == 1) return launch_k1_modes<128, 64, 4, 2, 4, 1>(ctx, a, P.b_kfast, P.a_kfast, true);
+  if (P.N <= 32 && P.M > 32) return launch_k1_modes<32, 64, 1, 2, 2, 2>(ctx, a, P.b_kfast, P.a_kfast, true);
+  if (P.M <= 32 && P.N > 32) return launch_k1_modes<64, 32, 2, 1, 2, 2>(ctx, a, P.b_kfast, P.a_kfast, true);
+  return launch_k1_modes<64, 64, 2, 2, 2, 2>(ctx, a, P.b_kfast, P.a_kfast, true);
 }
 
 int launch_pair(tncb_ctx* ctx, const PairPlan& P, const double2* A, const double2* B, double2* C) {
