@@ -69,6 +69,10 @@ void* tncb_ctx_stream(tncb_ctx* ctx);
 int tncb_ctx_stats(tncb_ctx* ctx, uint64_t* kernel_launches, uint64_t* arena_peak_bytes,
                    uint64_t* arena_live_bytes);
 int tncb_ctx_reset_stats(tncb_ctx* ctx);
+/* Dense-GEMM engine for large pairs: slices = 0 -> FP64 tensor pipe (DMMA, default);
+ * slices in [2,8] -> tcgen05 int8 path (exact digit slicing, 7 bits per slice; 8 slices cover the
+ * full 53-bit mantissa).  The environment variable TNCB_OZAKI_SLICES sets the default. */
+int tncb_ctx_set_tcgen05_slices(tncb_ctx* ctx, int slices);
 
 /* ---- tensors: replaces tetra::Tensor::{new_from_flat, elements, shape, ndim}
  *      (tnc/src/tensornetwork/tensordata.rs:31-37, tnc/src/io/hdf5.rs:105-106) ---- */

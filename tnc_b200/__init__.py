@@ -41,6 +41,10 @@ class Context:
         check(self._l.tncb_ctx_stats(self.handle, C.byref(a), C.byref(b), C.byref(c)))
         return {"kernel_launches": a.value, "arena_peak_bytes": b.value, "arena_live_bytes": c.value}
 
+    def set_tcgen05_slices(self, slices: int) -> None:
+        """0: FP64 tensor pipe (DMMA).  2..8: tcgen05 int8 digit slicing (K1') for large pairs."""
+        check(self._l.tncb_ctx_set_tcgen05_slices(self.handle, int(slices)))
+
     def reset_stats(self) -> None:
         check(self._l.tncb_ctx_reset_stats(self.handle))
 

@@ -75,6 +75,7 @@ struct tncb_ctx {
   cudaStream_t stream = nullptr;
   tncb::Arena arena;
   uint64_t launches = 0;
+  int oz_slices = 0;  // 0 = DMMA; 2..8 = tcgen05 int8 slicing (K1')
   int sm_count = 148;
   // pinned staging for leaf uploads
   void* stage_host = nullptr; size_t stage_bytes = 0;
@@ -96,6 +97,10 @@ int launch_permute(tncb_ctx* ctx, const double2* in, double2* out, int rank,
                    const uint64_t* in_dims, const int* perm);
 int launch_conj(tncb_ctx* ctx, double2* data, uint64_t elems);
 int ensure_tab(tncb_ctx* ctx, size_t elems);
+// K1': tcgen05 int8-sliced ZGEMM (ozaki.cu); tables as built by launch_k1
+int launch_k1_ozaki(tncb_ctx* ctx, const PairPlan& p, const double2* A, const double2* B, double2* C, int S,
+                    const long long* offAm, const long long* offBn, const long long* offAk, const long long* offBk);
+
 int ensure_partial(tncb_ctx* ctx, size_t elems);
 
 int tensor_new(tncb_ctx* ctx, int rank, const uint64_t* dims, tncb_tensor** out);

@@ -518,6 +518,9 @@ static int launch_k1(tncb_ctx* ctx, const PairPlan& P, const double2* A, const d
   a.A = A; a.B = B; a.C = C;
   a.offAm = ctx->tab; a.offBn = ctx->tab + P.M; a.offAk = ctx->tab + P.M + P.N; a.offBk = a.offAk + P.K;
   a.M = P.M; a.N = P.N; a.K = P.K;
+  // K1': the same contraction on tcgen05 (exact int8 slicing, ozaki.cu) for large GEMM-like pairs
+  if (ctx->oz_slices > 0 && P.M >= 256 && P.N >= 256 && P.K >= 256)
+    return launch_k1_ozaki(ctx, P, A, B, C, ctx->oz_slices, a.offAm, a.offBn, a.offAk, a.offBk);
   // Tile choice (A/B-measured on B200, C2 pair, profiles/r01_k1_tile_ab.txt): 64x64 tiles with a
   // 2-stage ring and 2 co-resident CTAs per SM reach ~90 % of the DMMA peak (independent CTAs
   // hide each other's per-chunk barrier/gather bubbles); 128x64 with 3-4 stages and 1 CTA/SM

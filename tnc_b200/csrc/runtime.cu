@@ -1,6 +1,7 @@
 // Context, device arena, tensor handles and the single-pair entry points of libtncb200.
 #include "internal.h"
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace tncb {
@@ -111,6 +112,7 @@ int tncb_ctx_create(int device, size_t arena_bytes, tncb_ctx** out) {
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
   ctx->arena.capacity_limit = arena_bytes;
+  if (const char* e = std::getenv("TNCB_OZAKI_SLICES")) ctx->oz_slices = std::max(0, std::min(8, atoi(e)));
   cudaError_t se = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (se != cudaSuccess) { delete ctx; return fail(TNCB_ERR_CUDA, cudaGetErrorString(se)); }
   // keep freed workspace memory in the stream-ordered pool
@@ -155,6 +157,13 @@ int tncb_ctx_stats(tncb_ctx* ctx, uint64_t* kernel_launches, uint64_t* arena_pea
 int tncb_ctx_reset_stats(tncb_ctx* ctx) {
   if (!ctx) return fail(TNCB_ERR_INVALID, "ctx is null");
   ctx->launches = 0; ctx->arena.peak = ctx->arena.live;
+  return TNCB_OK;
+}
+
+int tncb_ctx_set_tcgen05_slices(tncb_ctx* ctx, int slices) {
+  if (!ctx) return fail(TNCB_ERR_INVALID, "ctx is null");
+  if (slices != 0 && (slices < 2 || slices > 8)) return fail(TNCB_ERR_INVALID, "slices must be 0 or in [2, 8]");
+  ctx->oz_slices = slices;
   return TNCB_OK;
 }
 
