@@ -69,10 +69,16 @@ void* tncb_ctx_stream(tncb_ctx* ctx);
 int tncb_ctx_stats(tncb_ctx* ctx, uint64_t* kernel_launches, uint64_t* arena_peak_bytes,
                    uint64_t* arena_live_bytes);
 int tncb_ctx_reset_stats(tncb_ctx* ctx);
-/* Dense-GEMM engine for large pairs: slices = 0 -> FP64 tensor pipe (DMMA, default);
- * slices in [2,8] -> tcgen05 int8 path (exact digit slicing, 7 bits per slice; 8 slices cover the
- * full 53-bit mantissa).  The environment variable TNCB_OZAKI_SLICES sets the default. */
+/* Dense-GEMM engine for large pairs (K >= 1536 and >= 96 output tiles of 128x128):
+ * slices in [2,8] -> tcgen05 int8 path (exact 7-bit digit slicing; the default 8 slices cover the
+ * full 53-bit mantissa, measured |err| ~ 1e-15..7e-15 of max|C|, like FP64 accumulation itself);
+ * slices = 0 -> FP64 tensor pipe (DMMA) for every pair.  Smaller pairs always use DMMA / K0.
+ * The environment variable TNCB_OZAKI_SLICES overrides the default. */
 int tncb_ctx_set_tcgen05_slices(tncb_ctx* ctx, int slices);
+/* Measurement aid: bracket the dominant GEMM kernel of every large pair (k1_kernel / oz_gemm_kernel)
+ * with CUDA events on the ctx stream; tncb_ctx_last_gemm_ms synchronises and returns the last one. */
+int tncb_ctx_time_gemm(tncb_ctx* ctx, int enable);
+int tncb_ctx_last_gemm_ms(tncb_ctx* ctx, float* ms);
 
 /* ---- tensors: replaces tetra::Tensor::{new_from_flat, elements, shape, ndim}
  *      (tnc/src/tensornetwork/tensordata.rs:31-37, tnc/src/io/hdf5.rs:105-106) ---- */

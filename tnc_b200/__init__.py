@@ -45,6 +45,14 @@ class Context:
         """0: FP64 tensor pipe (DMMA).  2..8: tcgen05 int8 digit slicing (K1') for large pairs."""
         check(self._l.tncb_ctx_set_tcgen05_slices(self.handle, int(slices)))
 
+    def time_gemm(self, enable: bool = True) -> None:
+        check(self._l.tncb_ctx_time_gemm(self.handle, int(enable)))
+
+    def last_gemm_ms(self) -> float:
+        ms = C.c_float()
+        check(self._l.tncb_ctx_last_gemm_ms(self.handle, C.byref(ms)))
+        return float(ms.value)
+
     def reset_stats(self) -> None:
         check(self._l.tncb_ctx_reset_stats(self.handle))
 

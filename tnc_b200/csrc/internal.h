@@ -75,7 +75,8 @@ struct tncb_ctx {
   cudaStream_t stream = nullptr;
   tncb::Arena arena;
   uint64_t launches = 0;
-  int oz_slices = 0;  // 0 = DMMA; 2..8 = tcgen05 int8 slicing (K1')
+  int oz_slices = 8;  // 0 = DMMA only; 2..8 = tcgen05 int8 slicing (K1') for large pairs (8 = full mantissa)
+  bool time_gemm = false; cudaEvent_t gemm_ev0 = nullptr, gemm_ev1 = nullptr; bool gemm_ev_valid = false;
   int sm_count = 148;
   // pinned staging for leaf uploads
   void* stage_host = nullptr; size_t stage_bytes = 0;

@@ -453,7 +453,9 @@ static int launch_k1_cfg(tncb_ctx* ctx, const K1Args& a) {
   TNCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long tiles = (long long)a.tiles_m * a.tiles_n * a.ksplit;
   if (tiles > 0x7fffffffLL) return fail(TNCB_ERR_UNSUPPORTED, "K1 grid too large");
+  if (ctx->time_gemm) cudaEventRecord(ctx->gemm_ev0, ctx->stream);
   kern<<<(unsigned)tiles, WN * WM * 32, smem, ctx->stream>>>(a);
+  if (ctx->time_gemm) { cudaEventRecord(ctx->gemm_ev1, ctx->stream); ctx->gemm_ev_valid = true; }
   ctx->launches++;
   TNCB_CUDA(cudaGetLastError());
   return TNCB_OK;
@@ -519,8 +521,16 @@ static int launch_k1(tncb_ctx* ctx, const PairPlan& P, const double2* A, const d
   a.offAm = ctx->tab; a.offBn = ctx->tab + P.M; a.offAk = ctx->tab + P.M + P.N; a.offBk = a.offAk + P.K;
   a.M = P.M; a.N = P.N; a.K = P.K;
   // K1': the same contraction on tcgen05 (exact int8 slicing, ozaki.cu) for large GEMM-like pairs
-  if (ctx->oz_slices > 0 && P.M >= 256 && P.N >= 256 && P.K >= 256)
-    return launch_k1_ozaki(ctx, P, A, B, C, ctx->oz_slices, a.offAm, a.offBn, a.offAk, a.offBk);
+  if (ctx->oz_slices > 0 && P.M >= 256 && P.N >= 256 && P.K >= 256) {
+    static const bool force = std::getenv("TNCB_FORCE_TCGEN05") != nullptr;  // tuning aid: skip the size heuristic
+    const long long tiles = ((P.M + 127) / 128) * ((P.N + 127) / 128);
+    // crossover measured on B200 (profiles/r01_engine_sweep.txt): short K is dominated by the S
+    // FP64 read-modify-write flushes per tile, few tiles leave SMs idle (1 CTA per 128x128 tile)
+    if (force || (tiles >= 96 && P.K >= 1536) || (tiles >= 1024 && P.K >= 1024)) {
+      int rc = launch_k1_ozaki(ctx, P, A, B, C, ctx->oz_slices, a.offAm, a.offBn, a.offAk, a.offBk);
+      if (rc != TNCB_ERR_OOM) return rc;   // no room for the digit planes: fall through to the DMMA engine
+    }
+  }
   // Tile choice (A/B-measured on B200, C2 pair, profiles/r01_k1_tile_ab.txt): 64x64 tiles with a
   // 2-stage ring and 2 co-resident CTAs per SM reach ~90 % of the DMMA peak (independent CTAs
   // hide each other's per-chunk barrier/gather bubbles); 128x64 with 3-4 stages and 1 CTA/SM

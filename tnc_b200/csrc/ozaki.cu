@@ -367,7 +367,9 @@ int launch_k1_ozaki(tncb_ctx* ctx, const PairPlan& P, const double2* A, const do
   cudaError_t e = cudaFuncSetAttribute(oz_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   if (e != cudaSuccess) { cleanup(); return fail(TNCB_ERR_CUDA, cudaGetErrorString(e)); }
   dim3 grid((unsigned)(Mp / OZ_BT), (unsigned)(Np / OZ_BT));
+  if (ctx->time_gemm) cudaEventRecord(ctx->gemm_ev0, st);
   oz_gemm_kernel<<<grid, OZ_THREADS, smem_bytes, st>>>(mapB, mapA, a);
+  if (ctx->time_gemm) { cudaEventRecord(ctx->gemm_ev1, st); ctx->gemm_ev_valid = true; }
   ctx->launches++;
   e = cudaGetLastError();
   cleanup();  // stream-ordered reuse: later allocations are only touched by later kernels

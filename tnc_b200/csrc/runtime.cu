@@ -133,6 +133,7 @@ void tncb_ctx_destroy(tncb_ctx* ctx) {
   if (ctx->tab) cudaFree(ctx->tab);
   if (ctx->partial) cudaFree(ctx->partial);
   if (ctx->stage_host) cudaFreeHost(ctx->stage_host);
+  if (ctx->gemm_ev0) { cudaEventDestroy(ctx->gemm_ev0); cudaEventDestroy(ctx->gemm_ev1); }
   ctx->arena.release_all();
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -164,6 +165,22 @@ int tncb_ctx_set_tcgen05_slices(tncb_ctx* ctx, int slices) {
   if (!ctx) return fail(TNCB_ERR_INVALID, "ctx is null");
   if (slices != 0 && (slices < 2 || slices > 8)) return fail(TNCB_ERR_INVALID, "slices must be 0 or in [2, 8]");
   ctx->oz_slices = slices;
+  return TNCB_OK;
+}
+
+int tncb_ctx_time_gemm(tncb_ctx* ctx, int enable) {
+  if (!ctx) return fail(TNCB_ERR_INVALID, "ctx is null");
+  TNCB_CUDA(cudaSetDevice(ctx->device));
+  if (enable && !ctx->gemm_ev0) { TNCB_CUDA(cudaEventCreate(&ctx->gemm_ev0)); TNCB_CUDA(cudaEventCreate(&ctx->gemm_ev1)); }
+  ctx->time_gemm = enable != 0; ctx->gemm_ev_valid = false;
+  return TNCB_OK;
+}
+
+int tncb_ctx_last_gemm_ms(tncb_ctx* ctx, float* ms) {
+  if (!ctx || !ms) return fail(TNCB_ERR_INVALID, "null argument");
+  if (!ctx->gemm_ev_valid) return fail(TNCB_ERR_INVALID, "no timed GEMM kernel yet");
+  TNCB_CUDA(cudaEventSynchronize(ctx->gemm_ev1));
+  TNCB_CUDA(cudaEventElapsedTime(ms, ctx->gemm_ev0, ctx->gemm_ev1));
   return TNCB_OK;
 }
 
