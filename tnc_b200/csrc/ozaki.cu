@@ -129,6 +129,16 @@ __device__ __forceinline__ void oz_tma_2d(const CUtensorMap* map, uint64_t* bar,
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(oz_smem(smem)), "l"(map), "r"(oz_smem(bar)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void oz_tma_2d_mc(const CUtensorMap* map, uint64_t* bar, void* smem, int c0, int c1, uint16_t mask) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+               ::"r"(oz_smem(smem)), "l"(map), "r"(oz_smem(bar)), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void oz_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(oz_smem(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void oz_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // K-major SWIZZLE_128B canonical layout (cute UMMA SmemDescriptor): LBO=1, SBO=1024 B, version 1
 __device__ __forceinline__ uint64_t oz_desc(const void* smem) {
   uint64_t d = 0;
@@ -169,6 +179,11 @@ struct OzArgs {
   int S;
 };
 
+// CL = true: launched as 2x2 thread-block clusters.  The two CTAs of a cluster row work on the same
+// 128 Bt rows and the two of a column on the same 128 At rows, so every CTA loads only half of each
+// operand tile (64 rows) and TMA-multicasts it to its peer: L2->SM operand traffic per CTA drops
+// from 80 KB to 40 KB per stage (the non-cluster kernel is bound by exactly that traffic).
+template <bool CL>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 oz_gemm_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapA,
                const __grid_constant__ OzArgs p) {
@@ -183,8 +198,14 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant__
   const int kb_per_chunk = OZ_KCHUNK / OZ_BKB;
   const int nkc = (p.num_kb + kb_per_chunk - 1) / kb_per_chunk;
 
+  uint32_t crank = 0;
+  if (CL) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  const int cx = crank & 1, cy = (crank >> 1) & 1;   // cluster dims (2,2,1): rank = x + 2*y
+  // a stage may be refilled once this CTA *and* the peers that multicast into it... no: once every
+  // CTA that this CTA's producer writes to has consumed it: self, the x-peer (Bt halves), the y-peer (At halves)
+  const uint16_t free_mask = CL ? (uint16_t)((1u << crank) | (1u << (crank ^ 1)) | (1u << (crank ^ 2))) : 0;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < OZ_STAGES; s++) { oz_mbar_init(&full_bar[s], 1); oz_mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < OZ_STAGES; s++) { oz_mbar_init(&full_bar[s], 1); oz_mbar_init(&empty_bar[s], CL ? 3 : 1); }
     for (int b = 0; b < 2; b++) { oz_mbar_init(&tfull_bar[b], 1); oz_mbar_init(&tempty_bar[b], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -198,6 +219,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant__
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (CL) oz_cluster_sync();   // peers' barriers are initialised before any multicast / remote arrive
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_smem;
 
@@ -215,11 +237,23 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant__
             uint8_t* st = smem + s * OZ_STAGE_BYTES;
             oz_mbar_expect_tx(&full_bar[s], OZ_STAGE_BYTES);
             const int kx = kb * OZ_BKB;
-            oz_tma_2d(&mapB, &full_bar[s], st + 0 * OZ_TILE, kx, (0 * S + pp) * p.Np + n0);  // Br_p
-            oz_tma_2d(&mapB, &full_bar[s], st + 1 * OZ_TILE, kx, (1 * S + pp) * p.Np + n0);  // Bi_p
-            oz_tma_2d(&mapA, &full_bar[s], st + 2 * OZ_TILE, kx, (0 * S + qq) * p.Mp + m0);  // nAi_q
-            oz_tma_2d(&mapA, &full_bar[s], st + 3 * OZ_TILE, kx, (1 * S + qq) * p.Mp + m0);  // Ar_q
-            oz_tma_2d(&mapA, &full_bar[s], st + 4 * OZ_TILE, kx, (2 * S + qq) * p.Mp + m0);  // Ai_q
+            if (!CL) {
+              oz_tma_2d(&mapB, &full_bar[s], st + 0 * OZ_TILE, kx, (0 * S + pp) * p.Np + n0);  // Br_p
+              oz_tma_2d(&mapB, &full_bar[s], st + 1 * OZ_TILE, kx, (1 * S + pp) * p.Np + n0);  // Bi_p
+              oz_tma_2d(&mapA, &full_bar[s], st + 2 * OZ_TILE, kx, (0 * S + qq) * p.Mp + m0);  // nAi_q
+              oz_tma_2d(&mapA, &full_bar[s], st + 3 * OZ_TILE, kx, (1 * S + qq) * p.Mp + m0);  // Ar_q
+              oz_tma_2d(&mapA, &full_bar[s], st + 4 * OZ_TILE, kx, (2 * S + qq) * p.Mp + m0);  // Ai_q
+            } else {
+              // 64-row halves (box = 64 x 128 B); the SW128 layout keeps rows 0-63 / 64-127 in the first / second 8 KB
+              const uint16_t row_mask = (uint16_t)(0x3u << (2 * cy));                 // CTAs with the same n-tile
+              const uint16_t col_mask = (uint16_t)((1u << cx) | (1u << (cx + 2)));    // CTAs with the same m-tile
+              const int hb = cx * 64, ha = cy * 64;
+              oz_tma_2d_mc(&mapB, &full_bar[s], st + 0 * OZ_TILE + hb * OZ_BKB, kx, (0 * S + pp) * p.Np + n0 + hb, row_mask);
+              oz_tma_2d_mc(&mapB, &full_bar[s], st + 1 * OZ_TILE + hb * OZ_BKB, kx, (1 * S + pp) * p.Np + n0 + hb, row_mask);
+              oz_tma_2d_mc(&mapA, &full_bar[s], st + 2 * OZ_TILE + ha * OZ_BKB, kx, (0 * S + qq) * p.Mp + m0 + ha, col_mask);
+              oz_tma_2d_mc(&mapA, &full_bar[s], st + 3 * OZ_TILE + ha * OZ_BKB, kx, (1 * S + qq) * p.Mp + m0 + ha, col_mask);
+              oz_tma_2d_mc(&mapA, &full_bar[s], st + 4 * OZ_TILE + ha * OZ_BKB, kx, (2 * S + qq) * p.Mp + m0 + ha, col_mask);
+            }
           }
         }
       }
@@ -250,7 +284,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant__
               first = false;
               oz_umma_i8(acc, d_bi + ko, d_nai_ar + ko, idesc, 1u);               // (-Bi.Ai | Bi.Ar)
             }
-            oz_commit(&empty_bar[s]);
+            if (CL) oz_commit_mc(&empty_bar[s], free_mask); else oz_commit(&empty_bar[s]);
           }
         oz_commit(&tfull_bar[buf]);
       }
@@ -296,6 +330,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant__
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (CL) oz_cluster_sync();   // nobody leaves while a peer may still multicast into / signal this CTA
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
 }
 
@@ -316,12 +351,12 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-static int make_map(CUtensorMap* m, void* ptr, uint64_t rows, uint64_t kbytes) {
+static int make_map(CUtensorMap* m, void* ptr, uint64_t rows, uint64_t kbytes, uint32_t box_rows) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(TNCB_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
   cuuint64_t dims[2] = {kbytes, rows};
   cuuint64_t strides[1] = {kbytes};
-  cuuint32_t box[2] = {(cuuint32_t)OZ_BKB, (cuuint32_t)OZ_BT};
+  cuuint32_t box[2] = {(cuuint32_t)OZ_BKB, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -334,7 +369,13 @@ int launch_k1_ozaki(tncb_ctx* ctx, const PairPlan& P, const double2* A, const do
                     const long long* offAm, const long long* offBn, const long long* offAk, const long long* offBk) {
   if (S < 2) S = 2;
   if (S > OZ_MAX_S) S = OZ_MAX_S;
-  const long long Np = (P.N + OZ_BT - 1) / OZ_BT * OZ_BT, Mp = (P.M + OZ_BT - 1) / OZ_BT * OZ_BT;
+  // The 2x2 multicast variant is kept for the record but is OFF by default: measured on C2 it is
+  // slower (GEMM 10.3 ms vs 8.85 ms) although it halves the L2->SM operand traffic -- the kernel is
+  // bound by shared-memory bandwidth (UMMA operand reads 24 KB + TMA writes 20 KB per K-step = 172 B/clk
+  // against 128 B/clk), which multicast does not change; see profiles/r01_tcgen05_cluster_ab.txt.
+  static const bool cl = std::getenv("TNCB_OZ_CLUSTER") != nullptr;
+  const long long pad = cl ? 2 * OZ_BT : OZ_BT;   // 2x2 clusters need an even number of tiles per dimension
+  const long long Np = (P.N + pad - 1) / pad * pad, Mp = (P.M + pad - 1) / pad * pad;
   const long long Kp = (P.K + OZ_BKB - 1) / OZ_BKB * OZ_BKB;
   const size_t bytesB = (size_t)2 * S * Np * Kp, bytesA = (size_t)3 * S * Mp * Kp;
   const size_t bytesE = (size_t)(Np + Mp) * sizeof(int);
@@ -359,16 +400,29 @@ int launch_k1_ozaki(tncb_ctx* ctx, const PairPlan& P, const double2* A, const do
   }
   ctx->launches += 4;
   CUtensorMap mapB, mapA;
-  if ((rc = make_map(&mapB, pb, (uint64_t)2 * S * Np, (uint64_t)Kp)) || (rc = make_map(&mapA, pa, (uint64_t)3 * S * Mp, (uint64_t)Kp))) { cleanup(); return rc; }
+  const uint32_t box_rows = cl ? OZ_BT / 2 : OZ_BT;
+  if ((rc = make_map(&mapB, pb, (uint64_t)2 * S * Np, (uint64_t)Kp, box_rows)) || (rc = make_map(&mapA, pa, (uint64_t)3 * S * Mp, (uint64_t)Kp, box_rows))) { cleanup(); return rc; }
   OzArgs a;
   a.C = C; a.exp_n = exp_n; a.exp_m = exp_m; a.M = P.M; a.N = P.N; a.Np = (int)Np; a.Mp = (int)Mp;
   a.num_kb = (int)(Kp / OZ_BKB); a.S = S;
   const int smem_bytes = OZ_STAGES * OZ_STAGE_BYTES + 1024;
-  cudaError_t e = cudaFuncSetAttribute(oz_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  auto kern = cl ? oz_gemm_kernel<true> : oz_gemm_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   if (e != cudaSuccess) { cleanup(); return fail(TNCB_ERR_CUDA, cudaGetErrorString(e)); }
   dim3 grid((unsigned)(Mp / OZ_BT), (unsigned)(Np / OZ_BT));
   if (ctx->time_gemm) cudaEventRecord(ctx->gemm_ev0, st);
-  oz_gemm_kernel<<<grid, OZ_THREADS, smem_bytes, st>>>(mapB, mapA, a);
+  if (cl) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = dim3(OZ_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 2; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kern, mapB, mapA, a);
+    if (e != cudaSuccess) { cleanup(); return fail(TNCB_ERR_CUDA, std::string("cluster launch: ") + cudaGetErrorString(e)); }
+  } else {
+    kern<<<grid, OZ_THREADS, smem_bytes, st>>>(mapB, mapA, a);
+  }
   if (ctx->time_gemm) { cudaEventRecord(ctx->gemm_ev1, st); ctx->gemm_ev_valid = true; }
   ctx->launches++;
   e = cudaGetLastError();
