@@ -121,3 +121,51 @@ def test_path_independence(ctx):
     mapped = ContractionPath.simple([(n - 1 - i, n - 1 - j) for i, j in p.toplevel])
     b = complex(contract_tensor_network(tn, mapped, ctx=ctx).to_numpy())
     assert abs(a - b) <= 1e-10 * abs(a) + 1e-18
+
+
+def test_twelve_partitions_equal_flat(ctx):
+    """tnc/tests/integration_tests.rs:22-83: 15 qubits, 10 rounds, partitioned into 12 == flat
+    (KaHyPar replaced by the FM bisection restatement, StdRng by PCG64)."""
+    from tnc_b200.builders import random_circuit
+    from tnc_b200.tensornetwork import contract_tensor_network
+    from tnc_b200.tensornetwork.partitioning import find_partitioning, partition_tensor_network
+    tn = random_circuit(15, 10, 0.5, 0.5, np.random.default_rng(52), layout="line", layout_n=15)
+    flat = complex(contract_tensor_network(tn, greedy(tn), ctx=ctx).to_numpy())
+    part = find_partitioning(tn, 12, seed=3)
+    assert sorted(set(part)) == list(range(12))
+    ptn = partition_tensor_network(tn, part)
+    got = complex(contract_tensor_network(ptn, greedy(ptn), ctx=ctx).to_numpy())
+    assert abs(got - flat) <= 1e-9 * abs(flat) + 1e-14
+
+
+def test_sycamore_small_vs_oracle(ctx):
+    """builders/sycamore_circuit.rs:74-95 structure check + amplitude vs oracle."""
+    from collections import Counter
+    from tnc_b200.builders import sycamore_circuit
+    from tnc_b200.tensornetwork import contract_tensor_network
+    c = sycamore_circuit(3, 3, np.random.default_rng(42))
+    tn, _ = c.into_amplitude_network("000")
+    ranks = Counter(len(t.legs) for t in tn.tensors)
+    assert ranks == {1: 6, 2: 12, 4: 1}          # small_sycamore KAT
+    tn, _ = sycamore_circuit(12, 4, np.random.default_rng(7)).into_amplitude_network("0" * 12)
+    p = greedy(tn)
+    got = complex(contract_tensor_network(tn, p, ctx=ctx).to_numpy())
+    ref = complex(orc.contract_tensor_network(to_oracle(tn), to_opath(p)).data)
+    assert abs(got - ref) <= 1e-9 * abs(ref) + 1e-14
+
+
+def test_plan_graph_replay_matches_eager(ctx):
+    """K0-only plans replay as one CUDA graph; results must equal the eager executor bit for bit
+    (same kernels, same order) for every payload."""
+    from tnc_b200.builders import random_circuit_builder
+    from tnc_b200.tensornetwork import NetworkPlan, contract_tensor_network
+    c = random_circuit_builder(12, 6, 0.5, 0.5, np.random.default_rng(9))
+    tn0, _ = c.into_amplitude_network("0" * 12)
+    path = greedy(tn0)
+    plan = NetworkPlan(tn0, path, ctx=ctx)
+    for bits in ["0" * 12, "1" * 12, "010101010101", "000011110000"]:
+        c2 = random_circuit_builder(12, 6, 0.5, 0.5, np.random.default_rng(9))
+        tn, _ = c2.into_amplitude_network(bits)
+        a = complex(plan.execute(tn).to_numpy())
+        b = complex(contract_tensor_network(tn, path, ctx=ctx).to_numpy())
+        assert a == b, (bits, a, b)

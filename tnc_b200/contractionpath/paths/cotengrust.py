@@ -29,6 +29,7 @@ f32 = np.float32
 
 class OptMethod(Enum):
     Greedy = "greedy"
+    RandomGreedy = "random_greedy"   # OptMethod::RandomGreedy(ntrials), cotengrust.rs:69-83
 
 
 def _logadd(lx: f32, ly: f32) -> f32:
@@ -119,13 +120,17 @@ class _Processor:
     def contract(self, i: int, j: int) -> int:
         return self.contract_given_legs(i, j, self.compute_legs(self.nodes[i], self.nodes[j]))
 
-    def optimize_greedy(self, costmod: float = 1.0) -> None:
+    def optimize_greedy(self, costmod: float = 1.0, temperature: float = 0.0, rng=None) -> None:
         log_a = f32(np.log(f32(costmod), dtype=f32))
+        coeff_t = f32(temperature)
         node_size = {i: self.size(l) for i, l in self.nodes.items()}
         heap, contractions, c = [], {}, 0
 
         def score(sa, sb, sab):
-            return _logsub(sab, f32(_logadd(sa, sb) + log_a))
+            sc = _logsub(sab, f32(_logadd(sa, sb) + log_a))
+            if coeff_t != 0.0:  # Gumbel noise, as in cotengra's random-greedy
+                sc = f32(sc - coeff_t * f32(-np.log(-np.log(rng.random()))))
+            return sc
 
         for ix in sorted(self.edges):
             ns = sorted(self.edges[ix])
@@ -179,10 +184,66 @@ def optimize_greedy(inputs: List[List[int]], output: List[int], size_dict: Dict[
     return p.ssa_path
 
 
+def optimize_random_greedy(inputs, output, size_dict, ntrials: int, seed: int = 42, objective: str = "flops"):
+    """Random-greedy (cotengra): repeated greedy runs with a random cost modifier in [0, 50) (first trial: plain
+    greedy) and a log-uniform temperature in [0.001, 1]; keeps the path with the lowest flop count (or peak size).
+    The reference calls cotengrust's implementation (cotengrust.rs:69-83); RNG streams are not reproduced."""
+    rng = np.random.default_rng(seed)
+    best, best_cost = None, None
+    for trial in range(ntrials):
+        p = _Processor(inputs, output, size_dict)
+        if trial == 0:
+            p.optimize_greedy()
+        else:
+            costmod = float(rng.uniform(0.0, 50.0)) or 1e-3
+            temp = float(np.exp(rng.uniform(np.log(1e-3), np.log(1.0))))
+            p.optimize_greedy(max(costmod, 1e-3), temp, rng)
+        p.optimize_remaining_by_size()
+        cost = _ssa_path_cost(inputs, output, size_dict, p.ssa_path, objective)
+        if best_cost is None or cost < best_cost:
+            best, best_cost = p.ssa_path, cost
+    return best
+
+
+def _ssa_path_cost(inputs, output, size_dict, ssa_path, objective="flops"):
+    legs = {i: set(t) for i, t in enumerate(inputs)}
+    count: Dict[int, int] = {}
+    for t in inputs:
+        for l in t:
+            count[l] = count.get(l, 0) + 1
+    for l in output:
+        count[l] = count.get(l, 0) + 1
+    nxt, flops, peak = len(inputs), 0.0, 0.0
+    for (i, j) in ssa_path:
+        a, b = legs.pop(i), legs.pop(j)
+        allv = a | b
+        out = set()
+        for l in allv:
+            c = (l in a) + (l in b)
+            if c == count[l]:
+                continue
+            out.add(l)
+        for l in a & b:
+            count[l] -= 1
+        fl = 1.0
+        for l in allv:
+            fl *= size_dict[l]
+        sz = 1.0
+        for l in out:
+            sz *= size_dict[l]
+        flops += fl
+        peak = max(peak, sz)
+        legs[nxt] = out
+        nxt += 1
+    return flops if objective == "flops" else peak
+
+
 class Cotengrust:
-    def __init__(self, tensor: Tensor, opt_method: OptMethod = OptMethod.Greedy):
+    def __init__(self, tensor: Tensor, opt_method: OptMethod = OptMethod.Greedy, ntrials: int = 32, objective: str = "flops"):
         self.tensor = tensor
         self.opt_method = opt_method
+        self.ntrials = ntrials
+        self.objective = objective
         self.best_path = ContractionPath()
         self.best_flops = float("inf")
         self.best_size = float("inf")
@@ -191,6 +252,8 @@ class Cotengrust:
         if not inputs:
             return []
         size_dict = {l: float(d) for t in inputs for l, d in t.edges()}
+        if self.opt_method == OptMethod.RandomGreedy:
+            return optimize_random_greedy([list(t.legs) for t in inputs], list(output.legs), size_dict, self.ntrials, 42, self.objective)
         return optimize_greedy([list(t.legs) for t in inputs], list(output.legs), size_dict)
 
     def find_path(self) -> None:
@@ -199,7 +262,7 @@ class Cotengrust:
         inputs = list(self.tensor.tensors)
         for idx, t in enumerate(inputs):
             if t.is_composite():
-                ct = Cotengrust(t, self.opt_method)
+                ct = Cotengrust(t, self.opt_method, self.ntrials, self.objective)
                 ct.find_path()
                 nested[idx] = ct.get_best_path()
                 inputs[idx] = t.external_tensor()

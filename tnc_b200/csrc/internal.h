@@ -87,6 +87,7 @@ struct tncb_ctx {
   bool tab_valid = false; tncb::LegList tab_m{}, tab_n{}, tab_k{};
   // split-K partial workspace
   double2* partial = nullptr; size_t partial_elems = 0;
+  double2* partial_override = nullptr; size_t partial_override_elems = 0;  // set while a plan graph is captured
   // NCCL
   void* nccl_comm = nullptr; int world = 1, rank = 0;
 };
@@ -103,6 +104,7 @@ int launch_k1_ozaki(tncb_ctx* ctx, const PairPlan& p, const double2* A, const do
                     const long long* offAm, const long long* offBn, const long long* offAk, const long long* offBk);
 
 int ensure_partial(tncb_ctx* ctx, size_t elems);
+size_t k0_partial_elems(int sm_count, const PairPlan& p);
 
 int tensor_new(tncb_ctx* ctx, int rank, const uint64_t* dims, tncb_tensor** out);
 } // namespace tncb

@@ -404,11 +404,10 @@ static void launch_k0_g(dim3 grid, cudaStream_t st, const double2* A, const doub
   k0_kernel<G><<<grid, K0_THREADS, 0, st>>>(A, B, dst, a);
 }
 
-static int launch_k0(tncb_ctx* ctx, const PairPlan& P, const double2* A, const double2* B, double2* C) {
-  K0Args a;
-  a.m = P.m; a.n = P.n; a.k = P.k; a.M = P.M; a.N = P.N; a.K = P.K;
+// K0 launch geometry: G lanes per output, ksplit K ranges (deterministic two-pass reduction)
+void k0_config(int sm_count, const PairPlan& P, int* G_out, long long* ksplit_out, long long* kchunk_out) {
   const long long MN = P.M * P.N;
-  const long long target = (long long)ctx->sm_count * 1024; // lanes wanted in flight
+  const long long target = (long long)sm_count * 1024; // lanes wanted in flight
   int G = 1;
   while (G < 32 && MN * G < target && (long long)G * 2 <= P.K) G *= 2;
   long long ksplit = 1;
@@ -417,13 +416,34 @@ static int launch_k0(tncb_ctx* ctx, const PairPlan& P, const double2* A, const d
     ksplit = std::min(target / std::max(1LL, MN * G), per_lane / 32);
     ksplit = std::max(1LL, std::min(ksplit, 1024LL));
   }
-  a.kchunk = (P.K + ksplit - 1) / ksplit;
-  ksplit = (P.K + a.kchunk - 1) / a.kchunk;
+  const long long kchunk = (P.K + ksplit - 1) / ksplit;
+  ksplit = (P.K + kchunk - 1) / kchunk;
+  *G_out = G; *ksplit_out = ksplit; *kchunk_out = kchunk;
+}
+
+// elements of split-K scratch a K0 pair needs (0 = none); used by the CUDA-graph planner
+size_t k0_partial_elems(int sm_count, const PairPlan& P) {
+  int G; long long ksplit, kchunk;
+  k0_config(sm_count, P, &G, &ksplit, &kchunk);
+  return ksplit > 1 ? (size_t)(P.M * P.N * ksplit) : 0;
+}
+
+static int launch_k0(tncb_ctx* ctx, const PairPlan& P, const double2* A, const double2* B, double2* C) {
+  K0Args a;
+  a.m = P.m; a.n = P.n; a.k = P.k; a.M = P.M; a.N = P.N; a.K = P.K;
+  const long long MN = P.M * P.N;
+  int G; long long ksplit;
+  k0_config(ctx->sm_count, P, &G, &ksplit, &a.kchunk);
   double2* dst = C;
   if (ksplit > 1) {
-    int rc = ensure_partial(ctx, (size_t)(MN * ksplit));
-    if (rc) return rc;
-    dst = ctx->partial;
+    if (ctx->partial_override) {   // graph capture: plan-owned scratch with a fixed address
+      if ((size_t)(MN * ksplit) > ctx->partial_override_elems) return fail(TNCB_ERR_INVALID, "graph scratch too small");
+      dst = ctx->partial_override;
+    } else {
+      int rc = ensure_partial(ctx, (size_t)(MN * ksplit));
+      if (rc) return rc;
+      dst = ctx->partial;
+    }
   }
   const long long per_block = K0_THREADS / G;
   const long long blocks = (MN + per_block - 1) / per_block;

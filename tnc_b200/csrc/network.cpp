@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 
 namespace tncb {
 
@@ -264,7 +265,143 @@ static int execute(tncb_ctx* ctx, const Schedule& S, const tncb_tn* tn, tncb_ten
 
 } // namespace tncb
 
-struct tncb_plan { tncb::Schedule S; };
+// Compile once / execute many.  Plans whose steps are all K0 (the launch-bound regime: hundreds of
+// tiny pairs) get a static memory layout and are replayed as ONE CUDA graph: H2D of the staged
+// leaves + every pair kernel, no per-pair host work or launch gaps.
+struct tncb_plan {
+  tncb::Schedule S;
+  bool graphable = false;
+  std::vector<size_t> slot_off;      // byte offset of every slot in the workspace (graph mode)
+  size_t ws_bytes = 0, scratch_off = 0, scratch_elems = 0, leaf_off = 0;
+  tncb_ctx* ctx = nullptr;           // graph is tied to this context (stream, device)
+  void* ws = nullptr;                // arena block
+  void* stage = nullptr;             // plan-owned pinned staging of the leaf block
+  cudaGraphExec_t exec = nullptr;
+  uint64_t kernels_per_run = 0;
+};
+
+namespace tncb {
+
+// first-fit offset allocator with coalescing (same policy as the arena) for the static layout
+struct OffsetAlloc {
+  std::map<size_t, size_t> free_by_off; size_t top = 0;
+  static size_t up(size_t b) { return (std::max<size_t>(b, 256) + 255) / 256 * 256; }
+  size_t alloc(size_t bytes) {
+    bytes = up(bytes);
+    for (auto it = free_by_off.begin(); it != free_by_off.end(); ++it)
+      if (it->second >= bytes) {
+        size_t off = it->first, sz = it->second;
+        free_by_off.erase(it);
+        if (sz > bytes) free_by_off[off + bytes] = sz - bytes;
+        return off;
+      }
+    size_t off = top; top += bytes; return off;
+  }
+  void free(size_t off, size_t bytes) {
+    bytes = up(bytes);
+    auto it = free_by_off.emplace(off, bytes).first;
+    auto nx = std::next(it);
+    if (nx != free_by_off.end() && it->first + it->second == nx->first) { it->second += nx->second; free_by_off.erase(nx); }
+    if (it != free_by_off.begin()) { auto pv = std::prev(it); if (pv->first + pv->second == it->first) { pv->second += it->second; free_by_off.erase(it); } }
+  }
+};
+
+static void plan_static_layout(tncb_plan* P, int sm_count) {
+  const Schedule& S = P->S;
+  P->graphable = !S.steps.empty() && std::getenv("TNCB_NO_GRAPH") == nullptr;
+  for (int k : S.leaf_kind) if (k == TNCB_DATA_DEVICE) P->graphable = false;   // addresses change per call
+  size_t scratch = 0;
+  for (const Step& st : S.steps) {
+    if (st.plan.kernel_class != 0) { P->graphable = false; break; }
+    scratch = std::max(scratch, k0_partial_elems(sm_count, st.plan));
+  }
+  if (!P->graphable) return;
+  OffsetAlloc A;
+  P->leaf_off = A.alloc(std::max<size_t>(S.leaf_block_elems * sizeof(double2), 16));
+  P->scratch_elems = scratch;
+  P->scratch_off = scratch ? A.alloc(scratch * sizeof(double2)) : 0;
+  P->slot_off.assign(S.slots.size(), 0);
+  std::vector<size_t> sz(S.slots.size(), 0);
+  for (size_t s = 0; s < S.slots.size(); s++)
+    if (S.slots[s].leaf_index >= 0) P->slot_off[s] = P->leaf_off + S.leaf_offset[S.slots[s].leaf_index] * sizeof(double2);
+  for (const Step& st : S.steps) {
+    sz[st.out] = std::max<size_t>(S.slots[st.out].elems * sizeof(double2), 16);
+    P->slot_off[st.out] = A.alloc(sz[st.out]);
+    for (int s : {st.a, st.b}) if (sz[s]) { A.free(P->slot_off[s], sz[s]); sz[s] = 0; }
+  }
+  P->ws_bytes = A.top;
+  if (P->ws_bytes > ((size_t)1 << 30)) P->graphable = false;   // graphs are for small networks
+}
+
+static int stage_leaves(const Schedule& S, const std::vector<const tncb_tn*>& leaves, std::complex<double>* stage) {
+  for (size_t li = 0; li < leaves.size(); li++) {
+    const tncb_tn* lf = leaves[li];
+    if (S.leaf_kind[li] != lf->kind) return fail(TNCB_ERR_INVALID, "network payload kinds do not match the plan");
+    if (lf->kind == TNCB_DATA_GATE) {
+      int cnt = gate_matrix(lf->gate_name, lf->gate_angles, lf->n_gate_angles, lf->gate_adjoint != 0, stage + S.leaf_offset[li]);
+      if (cnt < 0) return cnt;
+    } else if (lf->kind == TNCB_DATA_MATRIX) {
+      uint64_t e = 1; for (int i = 0; i < lf->rank; i++) e *= lf->dims[i];
+      std::memcpy(stage + S.leaf_offset[li], lf->host_re_im, e * sizeof(double2));
+    }
+  }
+  return TNCB_OK;
+}
+
+static int execute_graph(tncb_ctx* ctx, tncb_plan* P, const tncb_tn* tn, tncb_tensor** out, int* n_out, uint64_t* out_legs) {
+  const Schedule& S = P->S;
+  TNCB_CUDA(cudaSetDevice(ctx->device));
+  std::vector<const tncb_tn*> leaves;
+  collect_leaf_nodes(tn, leaves);
+  if (leaves.size() != S.n_leaves_total) return fail(TNCB_ERR_INVALID, "network does not match the plan");
+  const size_t block_bytes = std::max<size_t>(S.leaf_block_elems * sizeof(double2), 16);
+  int rc;
+  if (!P->exec) {
+    P->ctx = ctx;
+    if ((rc = ctx->arena.alloc(P->ws_bytes, &P->ws))) return rc;
+    TNCB_CUDA(cudaMallocHost(&P->stage, block_bytes));
+  } else {
+    TNCB_CUDA(cudaStreamSynchronize(ctx->stream));   // the previous replay may still read the staging buffer
+  }
+  if ((rc = stage_leaves(S, leaves, (std::complex<double>*)P->stage))) return rc;
+  char* ws = (char*)P->ws;
+  if (!P->exec) {
+    cudaGraph_t graph = nullptr;
+    const uint64_t launches_before = ctx->launches;
+    TNCB_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    cudaMemcpyAsync(ws + P->leaf_off, P->stage, block_bytes, cudaMemcpyHostToDevice, ctx->stream);
+    ctx->partial_override = P->scratch_elems ? (double2*)(ws + P->scratch_off) : nullptr;
+    ctx->partial_override_elems = P->scratch_elems;
+    rc = TNCB_OK;
+    for (const Step& st : S.steps)
+      if ((rc = launch_pair(ctx, st.plan, (const double2*)(ws + P->slot_off[st.a]), (const double2*)(ws + P->slot_off[st.b]),
+                            (double2*)(ws + P->slot_off[st.out])))) break;
+    ctx->partial_override = nullptr; ctx->partial_override_elems = 0;
+    cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+    P->kernels_per_run = ctx->launches - launches_before;
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) return fail(TNCB_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
+    ce = cudaGraphInstantiate(&P->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) { P->exec = nullptr; return fail(TNCB_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(ce)); }
+    ctx->launches = launches_before;
+  }
+  TNCB_CUDA(cudaGraphLaunch(P->exec, ctx->stream));
+  ctx->launches += P->kernels_per_run;
+  tncb_tensor* result = nullptr;
+  if (S.result_slot >= 0) {
+    const SlotMeta& rm = S.slots[S.result_slot];
+    if ((rc = tensor_new(ctx, (int)rm.dims.size(), rm.dims.data(), &result))) return rc;
+    TNCB_CUDA(cudaMemcpyAsync(result->ptr, ws + P->slot_off[S.result_slot], rm.elems * sizeof(double2), cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  if (out) *out = result; else if (result) tncb_tensor_free(ctx, result);
+  if (n_out) *n_out = S.result_slot >= 0 ? (int)S.slots[S.result_slot].legs.size() : 0;
+  if (out_legs && S.result_slot >= 0)
+    for (size_t i = 0; i < S.slots[S.result_slot].legs.size(); i++) out_legs[i] = S.slots[S.result_slot].legs[i];
+  return TNCB_OK;
+}
+
+} // namespace tncb
 
 extern "C" {
 
@@ -283,12 +420,14 @@ int tncb_plan_create(tncb_ctx* ctx, const tncb_tn* tn, const tncb_path* path, tn
   tncb_plan* p = new tncb_plan();
   int rc = tncb::build_schedule(tn, path, p->S);
   if (rc) { delete p; return rc; }
+  tncb::plan_static_layout(p, ctx ? ctx->sm_count : 148);
   *out = p;
   return TNCB_OK;
 }
 
 int tncb_plan_execute(tncb_ctx* ctx, tncb_plan* plan, const tncb_tn* tn, tncb_tensor** out, int* n_out, uint64_t* out_legs) {
   if (!ctx || !plan || !tn) return tncb::fail(TNCB_ERR_INVALID, "null argument");
+  if (plan->graphable && (plan->ctx == nullptr || plan->ctx == ctx)) return tncb::execute_graph(ctx, plan, tn, out, n_out, out_legs);
   return tncb::execute(ctx, plan->S, tn, out, n_out, out_legs);
 }
 
@@ -316,6 +455,16 @@ int tncb_plan_info(const tncb_plan* plan, uint64_t* n_pairs, double* flops, doub
   return TNCB_OK;
 }
 
-void tncb_plan_destroy(tncb_plan* plan) { delete plan; }
+void tncb_plan_destroy(tncb_plan* plan) {
+  if (!plan) return;
+  if (plan->ctx) {
+    cudaSetDevice(plan->ctx->device);
+    cudaStreamSynchronize(plan->ctx->stream);
+    if (plan->exec) cudaGraphExecDestroy(plan->exec);
+    if (plan->ws) plan->ctx->arena.free(plan->ws, plan->ws_bytes);
+    if (plan->stage) cudaFreeHost(plan->stage);
+  }
+  delete plan;
+}
 
 } // extern "C"

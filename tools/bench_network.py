@@ -11,13 +11,27 @@ def main():
     ap.add_argument("--qubits", type=int, default=24); ap.add_argument("--rounds", type=int, default=12)
     ap.add_argument("--seed", type=int, default=1); ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--cpu", action="store_true"); ap.add_argument("--plan", action="store_true")
+    ap.add_argument("--circuit", default="random", choices=["random", "sycamore"])
+    ap.add_argument("--trials", type=int, default=0, help="random-greedy trials (0 = plain greedy)")
+    ap.add_argument("--path-file", default="", help="cache the replace-left path as JSON (path finding is not timed)")
     a = ap.parse_args()
     import tnc_b200 as tb
-    from tnc_b200.builders import random_circuit
-    from tnc_b200.contractionpath.paths import Cotengrust
+    from tnc_b200.builders import random_circuit, sycamore_circuit
+    from tnc_b200.contractionpath import ContractionPath
+    from tnc_b200.contractionpath.paths import Cotengrust, OptMethod
     from tnc_b200.tensornetwork import contract_tensor_network, NetworkPlan
-    tn = random_circuit(a.qubits, a.rounds, 0.5, 0.5, np.random.default_rng(a.seed))
-    opt = Cotengrust(tn); opt.find_path(); path = opt.get_best_replace_path()
+    if a.circuit == "sycamore":
+        tn = sycamore_circuit(a.qubits, a.rounds, np.random.default_rng(a.seed)).into_amplitude_network("0" * a.qubits)[0]
+    else:
+        tn = random_circuit(a.qubits, a.rounds, 0.5, 0.5, np.random.default_rng(a.seed))
+    if a.path_file and os.path.exists(a.path_file):
+        path = ContractionPath.simple([tuple(x) for x in json.load(open(a.path_file))["toplevel"]])
+    else:
+        opt = Cotengrust(tn, OptMethod.RandomGreedy, a.trials) if a.trials else Cotengrust(tn)
+        opt.find_path(); path = opt.get_best_replace_path()
+        if a.path_file:
+            json.dump({"network": f"{a.circuit} {a.qubits}q depth/rounds {a.rounds} seed {a.seed}", "finder": f"random-greedy {a.trials} trials" if a.trials else "greedy",
+                       "toplevel": path.toplevel}, open(a.path_file, "w"))
     ctx = tb.Context(0)
     plan = NetworkPlan(tn, path, ctx=ctx)
     info = plan.info()
@@ -29,7 +43,7 @@ def main():
         t0 = time.perf_counter(); r = run(); v = complex(r.to_numpy()); ts.append(time.perf_counter() - t0)
     st = ctx.stats()
     sec = float(np.median(ts))
-    out = {"network": f"random {a.qubits}q {a.rounds}r seed{a.seed}", "pairs": info["pairs"], "flops": info["flops"],
+    out = {"network": f"{a.circuit} {a.qubits}q {a.rounds}r seed{a.seed}", "pairs": info["pairs"], "flops": info["flops"],
            "peak_GiB": info["peak_bytes"] / 2**30, "gpu_ms": sec * 1e3, "gpu_ms_all": [round(t * 1e3, 3) for t in ts],
            "pairs_per_s": info["pairs"] / sec, "tflops": info["flops"] / sec * 1e-12, "amp": [amp.real, amp.imag],
            "launches_per_run": st["kernel_launches"] / a.steps, "arena_peak_GiB": st["arena_peak_bytes"] / 2**30, "plan_reuse": a.plan}
