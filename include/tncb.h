@@ -121,7 +121,8 @@ int tncb_pair_out_legs(int n_a, const uint64_t* a_legs, const uint64_t* a_dims,
                        int* n_out, uint64_t* out_legs, uint64_t* out_dims,
                        uint64_t* m, uint64_t* n, uint64_t* k);
 /* Which kernel class the planner would pick for that pair (no GPU):
- * 0 = K0 strided/warp-reduce kernel, 1 = K1 fused gather + DMMA ZGEMM. */
+ * 0 = K0 strided/warp-reduce kernel, 1 = K1 fused gather ZGEMM (DMMA, or tcgen05 K1' above the size
+ * threshold), 2 = K2 streaming kernel (big tensor x tiny tensor, HBM-bound). */
 int tncb_pair_kernel_class(int n_a, const uint64_t* a_legs, const uint64_t* a_dims,
                            int n_b, const uint64_t* b_legs, const uint64_t* b_dims);
 

@@ -114,6 +114,26 @@ def test_pairs_k0_streaming(ctx):
     check_pair(ctx, rng, big, [2] * 16, [15, 22], [2, 2])
 
 
+def test_pairs_k2_streaming_kernel(ctx, built_lib):
+    """K2 (big tensor x tiny tensor, HBM-bound): power-of-two and odd dims, both orientations,
+    N (or M) not a power of two, K = 1 (outer product with a big operand)."""
+    from tnc_b200._lib import u64_array
+    rng = np.random.default_rng(41)
+    def cls(a_legs, a_dims, b_legs, b_dims):
+        return built_lib.tncb_pair_kernel_class(len(a_legs), u64_array(a_legs), u64_array(a_dims), len(b_legs), u64_array(b_legs), u64_array(b_dims))
+    cases = [
+        (list(range(14)), [2] * 14, [3, 20, 9, 21], [2, 2, 2, 2]),            # big A, gate on legs 3 and 9
+        ([3, 20, 9, 21], [2, 2, 2, 2], list(range(14)), [2] * 14),            # big B
+        ([0, 1, 2, 3], [15, 17, 9, 33], [2, 9], [9, 3]),                      # odd dims: M = 15*17*33, N = 3, K = 9
+        ([9, 2], [3, 9], [0, 1, 2, 3], [15, 17, 9, 33]),                      # same, big B, M = 3
+        (list(range(13)), [2] * 13, [40], [5]),                               # K = 1: outer product, N = 5
+        ([0, 1, 2], [64, 64, 3], [2, 5, 6], [3, 2, 3]),                       # N = 6 (not a power of two)
+    ]
+    for a_legs, a_dims, b_legs, b_dims in cases:
+        assert cls(a_legs, a_dims, b_legs, b_dims) == 2, (a_legs, b_legs)
+        check_pair(ctx, rng, a_legs, a_dims, b_legs, b_dims)
+
+
 @pytest.mark.parametrize("mode", ["interleaved", "a_suffix_b_prefix", "a_prefix_b_suffix", "reversed"])
 def test_pairs_k1_modes(ctx, mode):
     """K1 (gather + DMMA ZGEMM) under the four loader-mode combinations, dims 2 and 4."""

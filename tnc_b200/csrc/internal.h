@@ -30,7 +30,8 @@ struct PairPlan {
   std::vector<uint64_t> out_legs, out_dims;
   long long M = 1, N = 1, K = 1;
   LegList m{}, n{}, k{};  // m: strides in A; n: strides in B (stored in .sa); k: sa=A, sb=B
-  int kernel_class = 0;   // 0 = K0, 1 = K1
+  int kernel_class = 0;   // 0 = K0, 1 = K1 (K1' above a size threshold), 2 = K2 streaming (big x tiny)
+  bool k2_big_is_a = true; // K2: which operand is the big one
   // K1 loader modes: true = consecutive threads walk the K index, false = the free index
   bool a_kfast = false, b_kfast = true;
   double flops() const { return 8.0 * (double)M * (double)N * (double)K; }

@@ -562,8 +562,113 @@ static int launch_k1(tncb_ctx* ctx, const PairPlan& P, const double2* A, const d
   return launch_k1_modes<64, 64, 2, 2, 2, 2>(ctx, a, P.b_kfast, P.a_kfast, true);
 }
 
+// ------------------------------------------------------------------------------------------
+// K2: streaming kernel for big x tiny pairs (HBM-bound).  thread <-> one index x of the big free
+// side; the tiny operand sits in shared memory as S[s][k]; every thread reads its K elements of the
+// big operand once and writes its NS outputs.  Algorithmic traffic 16*(BIG*K + BIG*SMALL) bytes.
+// ------------------------------------------------------------------------------------------
+struct K2Args {
+  LegList big;     // free legs of the big operand (strides in the big operand)
+  LegList sml;     // free legs of the tiny operand (strides in the tiny operand)
+  LegList k;       // shared legs: sa = stride in the big operand, sb = stride in the tiny operand
+  long long BIG, SMALL, K, M;   // M = row length of C
+  int big_is_a;    // 1: x = m (C[s*M + x]),  0: x = n (C[x*M + s])
+  int pow2;        // all big-side dims are powers of two -> shift/mask decomposition
+  int shift[kMaxGroups];
+};
+
+__device__ __forceinline__ long long decomp_shift(long long idx, const LegList& L, const int* sh) {
+  long long off = 0;
+  for (int g = L.n - 1; g > 0; --g) {
+    off += (idx & ((1LL << sh[g]) - 1)) * L.sa[g];
+    idx >>= sh[g];
+  }
+  if (L.n > 0) off += idx * L.sa[0];
+  return off;
+}
+
+template <int NS>
+__global__ void __launch_bounds__(256)
+k2_kernel(const double2* __restrict__ Big, const double2* __restrict__ Sml, double2* __restrict__ C,
+          const __grid_constant__ K2Args p) {
+  __shared__ double2 s_s[16 * 64];     // S[s][k], s < NS, k < K <= 64 ... NS*K <= 256 guaranteed by the planner
+  __shared__ long long s_kbig[64];
+  const int K = (int)p.K;
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {
+    long long ob, os;
+    decomp_ab(i, p.k, ob, os);
+    s_kbig[i] = ob;
+  }
+  for (int i = threadIdx.x; i < NS * K; i += blockDim.x) {
+    const int sidx = i / K, k = i - sidx * K;
+    double2 v = make_double2(0.0, 0.0);
+    if (sidx < p.SMALL) {
+      long long ob, os;
+      decomp_ab(k, p.k, ob, os);
+      v = __ldg(Sml + decomp_a(sidx, p.sml) + os);
+    }
+    s_s[i] = v;
+  }
+  __syncthreads();
+  for (long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x; x < p.BIG; x += (long long)gridDim.x * blockDim.x) {
+    const long long off = p.pow2 ? decomp_shift(x, p.big, p.shift) : decomp_a(x, p.big);
+    double ar[NS], ai[NS];
+#pragma unroll
+    for (int sI = 0; sI < NS; sI++) { ar[sI] = 0.0; ai[sI] = 0.0; }
+    for (int k = 0; k < K; k++) {
+      const double2 v = __ldg(Big + off + s_kbig[k]);
+#pragma unroll
+      for (int sI = 0; sI < NS; sI++) {
+        const double2 w = s_s[sI * K + k];   // broadcast
+        ar[sI] = fma(w.x, v.x, ar[sI]); ar[sI] = fma(-w.y, v.y, ar[sI]);
+        ai[sI] = fma(w.x, v.y, ai[sI]); ai[sI] = fma(w.y, v.x, ai[sI]);
+      }
+    }
+    if (p.big_is_a) {
+#pragma unroll
+      for (int sI = 0; sI < NS; sI++)
+        if (sI < p.SMALL) C[(long long)sI * p.M + x] = make_double2(ar[sI], ai[sI]);
+    } else {
+      double2* dst = C + x * p.M;
+#pragma unroll
+      for (int sI = 0; sI < NS; sI++)
+        if (sI < p.SMALL) dst[sI] = make_double2(ar[sI], ai[sI]);
+    }
+  }
+}
+
+static int launch_k2(tncb_ctx* ctx, const PairPlan& P, const double2* A, const double2* B, double2* C) {
+  K2Args a;
+  const bool big_a = P.k2_big_is_a;
+  a.big = big_a ? P.m : P.n;
+  a.sml = big_a ? P.n : P.m;
+  a.k = P.k;
+  if (!big_a) for (int g = 0; g < a.k.n; g++) std::swap(a.k.sa[g], a.k.sb[g]);   // sa = big operand's stride
+  a.BIG = big_a ? P.M : P.N; a.SMALL = big_a ? P.N : P.M; a.K = P.K; a.M = P.M; a.big_is_a = big_a ? 1 : 0;
+  a.pow2 = 1;
+  for (int g = 0; g < a.big.n; g++) {
+    const long long d = a.big.dim[g];
+    if (d & (d - 1)) { a.pow2 = 0; a.shift[g] = 0; } else { int sh = 0; while ((1LL << sh) < d) sh++; a.shift[g] = sh; }
+  }
+  const double2* Big = big_a ? A : B;
+  const double2* Sml = big_a ? B : A;
+  const int blocks = (int)std::min<long long>((a.BIG + 255) / 256, (long long)ctx->sm_count * 32);
+  int ns = 1; while (ns < a.SMALL) ns *= 2;
+  switch (ns) {
+    case 1: k2_kernel<1><<<blocks, 256, 0, ctx->stream>>>(Big, Sml, C, a); break;
+    case 2: k2_kernel<2><<<blocks, 256, 0, ctx->stream>>>(Big, Sml, C, a); break;
+    case 4: k2_kernel<4><<<blocks, 256, 0, ctx->stream>>>(Big, Sml, C, a); break;
+    case 8: k2_kernel<8><<<blocks, 256, 0, ctx->stream>>>(Big, Sml, C, a); break;
+    default: k2_kernel<16><<<blocks, 256, 0, ctx->stream>>>(Big, Sml, C, a); break;
+  }
+  ctx->launches++;
+  TNCB_CUDA(cudaGetLastError());
+  return TNCB_OK;
+}
+
 int launch_pair(tncb_ctx* ctx, const PairPlan& P, const double2* A, const double2* B, double2* C) {
   if (P.M * P.N == 0) return TNCB_OK;
+  if (P.kernel_class == 2) return launch_k2(ctx, P, A, B, C);
   if (P.kernel_class == 1) return launch_k1(ctx, P, A, B, C);
   return launch_k0(ctx, P, A, B, C);
 }

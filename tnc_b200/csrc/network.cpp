@@ -312,8 +312,8 @@ static void plan_static_layout(tncb_plan* P, int sm_count) {
   for (int k : S.leaf_kind) if (k == TNCB_DATA_DEVICE) P->graphable = false;   // addresses change per call
   size_t scratch = 0;
   for (const Step& st : S.steps) {
-    if (st.plan.kernel_class != 0) { P->graphable = false; break; }
-    scratch = std::max(scratch, k0_partial_elems(sm_count, st.plan));
+    if (st.plan.kernel_class == 1) { P->graphable = false; break; }   // K1/K1' use ctx-owned tables / arena scratch
+    if (st.plan.kernel_class == 0) scratch = std::max(scratch, k0_partial_elems(sm_count, st.plan));
   }
   if (!P->graphable) return;
   OffsetAlloc A;
@@ -449,7 +449,7 @@ int tncb_plan_info(const tncb_plan* plan, uint64_t* n_pairs, double* flops, doub
   }
   if (n_kernels) {
     uint64_t k = 0;
-    for (const tncb::Step& st : S.steps) k += st.plan.kernel_class == 1 ? 2 : 1;
+    for (const tncb::Step& st : S.steps) k += st.plan.kernel_class == 1 ? 2 : 1;  // (K1: table build + GEMM)
     *n_kernels = k;
   }
   return TNCB_OK;

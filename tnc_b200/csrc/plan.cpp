@@ -96,6 +96,13 @@ int plan_pair(int n_a, const uint64_t* a_legs, const uint64_t* a_dims,
   bool gemm_like = P.M >= 16 && P.N >= 16 && P.K >= 4 &&
                    (double)P.M * (double)P.N * (double)P.K >= (double)(1 << 17);
   P.kernel_class = gemm_like ? 1 : 0;
+  // K2: "gate application" shapes -- a big tensor against a tiny one (low arithmetic intensity,
+  // HBM-bound).  One thread owns one index of the big free side and produces all outputs of the
+  // small side, so the big operand is read exactly once.
+  if (P.K <= 64) {
+    if (P.N <= 16 && P.N * P.K <= 256 && P.M >= 4096) { P.kernel_class = 2; P.k2_big_is_a = true; }
+    else if (P.M <= 16 && P.M * P.K <= 256 && P.N >= 4096) { P.kernel_class = 2; P.k2_big_is_a = false; }
+  }
   return TNCB_OK;
 }
 
@@ -121,7 +128,7 @@ const char* tncb_strerror(int status) {
   }
 }
 
-const char* tncb_version(void) { return "libtncb200 0.1 (sm_100a; K0 strided/warp-reduce, K1 gather+DMMA ZGEMM)"; }
+const char* tncb_version(void) { return "libtncb200 0.2 (sm_100a; K0 strided/split-K, K1 gather+DMMA ZGEMM, K1' tcgen05 int8 digit slicing, K2 streaming)"; }
 
 int tncb_pair_out_legs(int n_a, const uint64_t* a_legs, const uint64_t* a_dims,
                        int n_b, const uint64_t* b_legs, const uint64_t* b_dims,

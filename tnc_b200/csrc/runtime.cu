@@ -1,6 +1,7 @@
 // Context, device arena, tensor handles and the single-pair entry points of libtncb200.
 #include "internal.h"
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -38,6 +39,8 @@ int Arena::alloc(size_t bytes, void** out) {
   if (e != cudaSuccess && want > bytes) { cudaGetLastError(); want = bytes; e = cudaMalloc(&p, want); }
   if (e != cudaSuccess) { cudaGetLastError(); return fail(TNCB_ERR_OOM, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
   reserved += want;
+  if (std::getenv("TNCB_TRACE")) fprintf(stderr, "TNCB_TRACE arena: new slab %.1f MiB for a %.1f MiB request (reserved %.1f MiB, live %.1f MiB)\n",
+                                         want / 1048576.0, bytes / 1048576.0, reserved / 1048576.0, live / 1048576.0);
   next_slab = std::min(next_slab * 2, (size_t)16 << 30);
   Slab s; s.base = (char*)p; s.size = want;
   if (want > bytes) s.free_by_off[bytes] = want - bytes;
