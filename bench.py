@@ -174,6 +174,54 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def network_c4(tb, ctx, rank, world, dist, torch, local):
+    """BASELINE config 4's network (36-qubit random-circuit amplitude, 10 rounds, greedy path, 488 pairs) through
+    contract_tensor_network: flat on one GPU, or -- with N > 1 ranks -- 8 slices (the reference's "future work"
+    data-parallel mode) spread over the ranks with ONE ncclAllReduce at the end.  Timed region as in
+    benchmark/src/main.rs:355-360: path finding / slice finding excluded, leaf materialisation + H2D + D2H included."""
+    from tnc_b200.builders import random_circuit
+    from tnc_b200.contractionpath.paths import Cotengrust
+    from tnc_b200.contractionpath.slicing import contract_sliced, find_slices, path_cost
+    from tnc_b200.tensornetwork import contract_tensor_network
+    tn = random_circuit(36, 10, 0.5, 0.5, np.random.default_rng(1))      # same seed on every rank -> same network
+    opt = Cotengrust(tn); opt.find_path(); path = opt.get_best_replace_path()
+    meta = [(t.legs, t.bond_dims) for t in tn.tensors]
+    flops_flat = path_cost(meta, path)[0]
+    out = {"network": "random-circuit amplitude, 36 qubits, 10 rounds, Sycamore coupling, greedy path", "pairs": len(path.toplevel),
+           "flops_flat": flops_flat}
+    def timed(fn, reps=3):
+        ts = []
+        for _ in range(reps):
+            if world > 1:
+                dist.barrier()
+            ctx.synchronize(); t0 = time.perf_counter()
+            amp = complex(fn().to_numpy())
+            dt = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dt], device=f"cuda:{local}", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t.item())
+            ts.append(dt)
+        return float(np.median(ts)), amp
+    if world == 1:
+        sec, amp = timed(lambda: contract_tensor_network(tn, path, ctx=ctx))
+        out.update({"mode": "flat", "ms": sec * 1e3, "pairs_per_s": len(path.toplevel) / sec, "zgemm_tflops": flops_flat / sec * 1e-12,
+                    "amplitude": [amp.real, amp.imag]})
+        legs = find_slices(tn, path, min_slices=8)
+        sec8, amp8 = timed(lambda: contract_sliced(tn, path, legs, ctx=ctx))
+        out["sliced8_on_1gpu"] = {"ms": sec8 * 1e3, "rel_diff_vs_flat": abs(amp8 - amp) / abs(amp)}
+    else:
+        from tnc_b200.dist import init_device_comm
+        init_device_comm(ctx)
+        legs = find_slices(tn, path, min_slices=8)
+        fs = path_cost(meta, path, legs)[0]
+        sec, amp = timed(lambda: contract_sliced(tn, path, legs, ctx=ctx, rank=rank, world=world))
+        n_sl = 2 ** len(legs)
+        out.update({"mode": f"sliced: {n_sl} slices round-robin over {world} ranks + 1 ncclAllReduce", "ms": sec * 1e3,
+                    "pairs_per_s": len(path.toplevel) * n_sl / sec, "zgemm_tflops": fs * n_sl / sec * 1e-12,
+                    "flops_per_slice": fs, "amplitude": [amp.real, amp.imag]})
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -344,6 +392,16 @@ def run_ours(args):
         }
         if cpu:
             line["cpu_baseline"] = cpu
+    # extra object: the named 36-qubit network (strong scaling by slicing when N > 1); never fatal
+    net = None
+    if not args.no_network:
+        try:
+            net = network_c4(tb, ctx, rank, world, dist, torch, local)
+        except Exception as e:  # keep the headline line even if the extra leg fails
+            net = {"error": f"{type(e).__name__}: {e}"}
+    if rank == 0:
+        if net is not None:
+            line["network_c4"] = net
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -371,6 +429,7 @@ def main():
     ap.add_argument("--workload", default="pair")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel-only", action="store_true", help="tuning aid: skip the e2e and CPU legs")
+    ap.add_argument("--no-network", action="store_true", help="skip the network_c4 extra object")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -131,6 +131,9 @@ int tncb_pair_kernel_class(int n_a, const uint64_t* a_legs, const uint64_t* a_di
 /* out dims[i] = in dims[perm[i]] (numpy.transpose semantics); consumes `t`. */
 int tncb_permute(tncb_ctx* ctx, tncb_tensor* t, const int* perm, tncb_tensor** out);
 int tncb_conjugate(tncb_ctx* ctx, tncb_tensor* t); /* in place */
+/* dst += src (same element count): accumulation of sliced contractions (the reference's declared
+ * future work, book/src/future_work.md:9-11). */
+int tncb_tensor_add(tncb_ctx* ctx, tncb_tensor* dst, const tncb_tensor* src);
 
 /* ---- gate table: replaces load_gate / load_gate_adjoint (tnc/src/gates.rs:50-66).
  *      Host-side; writes 4 or 16 interleaved complex values, *rank = 2 or 4. ---- */
@@ -199,6 +202,8 @@ int tncb_comm_unique_id(uint8_t id_out[128]);
 int tncb_comm_init(tncb_ctx* ctx, int world_size, int rank, const uint8_t id[128]);
 int tncb_comm_send(tncb_ctx* ctx, const tncb_tensor* t, int peer);
 int tncb_comm_recv(tncb_ctx* ctx, int rank_dims, const uint64_t* dims, int peer, tncb_tensor** out);
+/* In-place sum over all ranks (ncclAllReduce on the ctx stream): combines sliced contractions. */
+int tncb_comm_allreduce_sum(tncb_ctx* ctx, tncb_tensor* t);
 int tncb_comm_destroy(tncb_ctx* ctx);
 /* get_tensor_mapping (mpi/communication.rs:89-115): partition -> rank, the
  * partition on the left of the last top-level pair goes to rank 0, the others

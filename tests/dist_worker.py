@@ -75,8 +75,20 @@ def gpu_main():
             amp = complex(res.to_numpy())
         ctx.synchronize(); dist.barrier()
         dt = time.perf_counter() - t0
+    # slicing over ranks with one NCCL all-reduce
+    from tnc_b200.contractionpath.slicing import contract_sliced, find_slices
+    from tnc_b200.dist import broadcast_serializing
+    spec = None
+    if rank == 0:
+        spec = (tn, fpath, find_slices(tn, fpath, min_slices=max(4, world)))
+    stn, spath, legs = broadcast_serializing(spec, 0)
+    dist.barrier(); ctx.synchronize(); t0 = time.perf_counter()
+    sres = contract_sliced(stn, spath, legs, ctx=ctx, rank=rank, world=world)
+    samp = complex(sres.to_numpy()); ts = time.perf_counter() - t0
     if rank == 0:
         t0 = time.perf_counter(); flat = complex(contract_tensor_network(tn, fpath, ctx=ctx).to_numpy()); tf = time.perf_counter() - t0
+        print(f"SLICED_OK world={world} slices={2 ** len(legs)} sliced={samp} abs_err={abs(samp - flat):.3e} t_sliced={ts*1e3:.2f}ms", flush=True)
+        assert abs(samp - flat) <= 1e-9 * abs(flat) + 1e-14
         err = abs(amp - flat)
         print(f"DIST_OK world={world} q={q} r={r} partitioned={amp} flat={flat} abs_err={err:.3e} t_part={dt*1e3:.2f}ms t_flat={tf*1e3:.2f}ms", flush=True)
         assert err <= 1e-9 * abs(flat) + 1e-14

@@ -46,4 +46,4 @@ def test_nccl_fanin_equals_flat():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(free_port()), os.path.join(ROOT, "tests", "dist_worker.py")]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
-    assert r.returncode == 0 and "DIST_OK" in r.stdout, r.stdout[-3000:]
+    assert r.returncode == 0 and "DIST_OK" in r.stdout and "SLICED_OK" in r.stdout, r.stdout[-3000:]

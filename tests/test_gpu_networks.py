@@ -169,3 +169,30 @@ def test_plan_graph_replay_matches_eager(ctx):
         a = complex(plan.execute(tn).to_numpy())
         b = complex(contract_tensor_network(tn, path, ctx=ctx).to_numpy())
         assert a == b, (bits, a, b)
+
+
+def test_sliced_equals_flat(ctx):
+    """Slicing (book/src/future_work.md:9-11): the sum over slices equals the unsliced contraction,
+    also for an open (statevector) result accumulated on the device."""
+    from tnc_b200.builders import random_circuit, random_circuit_builder
+    from tnc_b200.contractionpath.slicing import contract_sliced, find_slices, path_cost
+    from tnc_b200.tensornetwork import contract_tensor_network
+    tn = random_circuit(16, 8, 0.5, 0.5, np.random.default_rng(3))
+    p = greedy(tn)
+    flat = complex(contract_tensor_network(tn, p, ctx=ctx).to_numpy())
+    for ms in (2, 8):
+        legs = find_slices(tn, p, min_slices=ms)
+        assert 2 ** len(legs) >= ms
+        got = complex(contract_sliced(tn, p, legs, ctx=ctx).to_numpy())
+        assert abs(got - flat) <= 1e-10 * abs(flat) + 1e-14
+    meta = [(t.legs, t.bond_dims) for t in tn.tensors]
+    legs = find_slices(tn, p, min_slices=1, max_peak_elements=path_cost(meta, p)[1] / 4)
+    assert path_cost(meta, p, legs)[1] <= path_cost(meta, p)[1] / 4          # memory-bounded slicing
+    c = random_circuit_builder(8, 5, 0.5, 0.5, np.random.default_rng(4))
+    tn, perm = c.into_statevector_network()
+    p = greedy(tn)
+    ref = contract_tensor_network(tn, p, ctx=ctx)
+    legs = find_slices(tn, p, min_slices=4)
+    got = contract_sliced(tn, p, legs, ctx=ctx)
+    assert got.legs == ref.legs
+    assert np.abs(got.to_numpy() - ref.to_numpy()).max() <= 1e-12

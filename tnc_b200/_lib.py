@@ -78,6 +78,7 @@ SIGNATURES = {
     "tncb_pair_kernel_class": (C.c_int, [C.c_int, u64p, u64p, C.c_int, u64p, u64p]),
     "tncb_permute": (C.c_int, [C.c_void_p, C.c_void_p, i32p, vpp]),
     "tncb_conjugate": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "tncb_tensor_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "tncb_gate_matrix": (C.c_int, [C.c_char_p, f64p, C.c_int, C.c_int, f64p, i32p]),
     "tncb_contract_tensor_network": (C.c_int, [C.c_void_p, C.POINTER(TncbTn), C.POINTER(TncbPath), vpp, i32p, u64p]),
     "tncb_plan_create": (C.c_int, [C.c_void_p, C.POINTER(TncbTn), C.POINTER(TncbPath), vpp]),
@@ -88,6 +89,7 @@ SIGNATURES = {
     "tncb_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "tncb_comm_send": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "tncb_comm_recv": (C.c_int, [C.c_void_p, C.c_int, u64p, C.c_int, vpp]),
+    "tncb_comm_allreduce_sum": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tncb_comm_destroy": (C.c_int, [C.c_void_p]),
     "tncb_fanin_mapping": (C.c_int, [C.c_size_t, u64p, C.c_size_t, u64p, C.c_int, i32p]),
 }

@@ -26,6 +26,7 @@ struct NcclFns {
   const char* (*GetErrorString)(int) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
 };
 
 static NcclFns g_nccl;
@@ -53,6 +54,7 @@ static void load_nccl() {
   LOAD(GetErrorString, "ncclGetErrorString");
   LOAD(GroupStart, "ncclGroupStart");
   LOAD(GroupEnd, "ncclGroupEnd");
+  LOAD(AllReduce, "ncclAllReduce");
 #undef LOAD
 }
 
@@ -117,6 +119,14 @@ int tncb_comm_recv(tncb_ctx* ctx, int rank_dims, const uint64_t* dims, int peer,
   int r = g_nccl.Recv(t->ptr, (size_t)t->elems * 2, kNcclFloat64, peer, ctx->nccl_comm, ctx->stream);
   if (r != 0) { tncb_tensor_free(ctx, t); return fail(TNCB_ERR_NCCL, std::string("ncclRecv: ") + g_nccl.GetErrorString(r)); }
   *out = t;
+  return TNCB_OK;
+}
+
+int tncb_comm_allreduce_sum(tncb_ctx* ctx, tncb_tensor* t) {
+  if (!ctx || !t) return fail(TNCB_ERR_INVALID, "null argument");
+  if (!ctx->nccl_comm) return fail(TNCB_ERR_NCCL, "communicator not initialised");
+  TNCB_CUDA(cudaSetDevice(ctx->device));
+  TNCB_NCCL(g_nccl.AllReduce(t->ptr, t->ptr, (size_t)t->elems * 2, kNcclFloat64, /*ncclSum*/ 0, ctx->nccl_comm, ctx->stream));
   return TNCB_OK;
 }
 

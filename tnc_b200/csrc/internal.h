@@ -99,6 +99,7 @@ int launch_pair(tncb_ctx* ctx, const PairPlan& p, const double2* A, const double
 int launch_permute(tncb_ctx* ctx, const double2* in, double2* out, int rank,
                    const uint64_t* in_dims, const int* perm);
 int launch_conj(tncb_ctx* ctx, double2* data, uint64_t elems);
+int launch_add(tncb_ctx* ctx, double2* dst, const double2* src, uint64_t elems);
 int ensure_tab(tncb_ctx* ctx, size_t elems);
 // K1': tcgen05 int8-sliced ZGEMM (ozaki.cu); tables as built by launch_k1
 int launch_k1_ozaki(tncb_ctx* ctx, const PairPlan& p, const double2* A, const double2* B, double2* C, int S,

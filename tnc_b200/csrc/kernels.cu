@@ -697,6 +697,22 @@ int launch_permute(tncb_ctx* ctx, const double2* in, double2* out, int rank,
   return TNCB_OK;
 }
 
+__global__ void add_kernel(double2* __restrict__ dst, const double2* __restrict__ src, long long total) {
+  for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (long long)gridDim.x * blockDim.x) {
+    double2 d = dst[o]; const double2 v = src[o];
+    d.x += v.x; d.y += v.y; dst[o] = d;
+  }
+}
+
+int launch_add(tncb_ctx* ctx, double2* dst, const double2* src, uint64_t elems) {
+  if (elems == 0) return TNCB_OK;
+  const int blocks = (int)std::min<long long>(((long long)elems + 255) / 256, (long long)ctx->sm_count * 16);
+  add_kernel<<<blocks, 256, 0, ctx->stream>>>(dst, src, (long long)elems);
+  ctx->launches++;
+  TNCB_CUDA(cudaGetLastError());
+  return TNCB_OK;
+}
+
 int launch_conj(tncb_ctx* ctx, double2* data, uint64_t elems) {
   if (elems == 0) return TNCB_OK;
   const int blocks = (int)std::min<long long>(((long long)elems + 255) / 256, (long long)ctx->sm_count * 16);

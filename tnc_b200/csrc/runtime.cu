@@ -318,6 +318,13 @@ int tncb_permute(tncb_ctx* ctx, tncb_tensor* t, const int* perm, tncb_tensor** o
   return TNCB_OK;
 }
 
+int tncb_tensor_add(tncb_ctx* ctx, tncb_tensor* dst, const tncb_tensor* src) {
+  if (!ctx || !dst || !src) return fail(TNCB_ERR_INVALID, "null argument");
+  if (dst->elems != src->elems) return fail(TNCB_ERR_SHAPE, "tensor_add: element counts differ");
+  TNCB_CUDA(cudaSetDevice(ctx->device));
+  return launch_add(ctx, dst->ptr, src->ptr, dst->elems);
+}
+
 int tncb_conjugate(tncb_ctx* ctx, tncb_tensor* t) {
   if (!ctx || !t) return fail(TNCB_ERR_INVALID, "null argument");
   TNCB_CUDA(cudaSetDevice(ctx->device));
