@@ -14,6 +14,10 @@ def build_case(qubits=10, rounds=6, seed=22, parts=2):
     from tnc_b200.tensornetwork.partitioning import find_partitioning, partition_tensor_network
     tn = random_circuit(qubits, rounds, 0.5, 0.5, np.random.default_rng(seed))
     part = find_partitioning(tn, parts, seed=1)
+    sa_steps = int(os.environ.get("TNCB_SA", "0"))
+    if sa_steps:   # refine like the reference's SA balancer (step-budget, seeded)
+        from tnc_b200.contractionpath.repartitioning import balance_partitions
+        part, _ = balance_partitions(tn, parts, part, steps=sa_steps, seed=1)
     ptn = partition_tensor_network(tn, part)
     opt = Cotengrust(ptn); opt.find_path()
     flat = Cotengrust(tn); flat.find_path()

@@ -1,0 +1,145 @@
+"""Partition evaluation and refinement: mirrors tnc::contractionpath::repartitioning
+(`compute_solution`, repartitioning.rs:25-76) and the simulated-annealing balancer
+(repartitioning/simulated_annealing.rs: `evaluate_partitioning` :185-214, the intermediate-tensor move
+model :251-352, acceptance rule :118-127, temperatures 2.0 -> 0.05 :583-590).
+
+Planning only (metadata): the output -- a partition vector -- is an *input* of the partitioned
+contraction.  Differences to the reference, on purpose: the annealing schedule is driven by a
+*step budget* instead of wall-clock time and uses one seeded chain instead of 48 rayon chains, so a
+seed reproduces a partitioning (the reference's result depends on machine speed, :107,153-160)."""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from ..tensornetwork.partitioning import partition_tensor_network
+from ..tensornetwork.tensor import Tensor
+from . import ContractionPath
+from .contraction_cost import contract_op_cost_tensors, contract_path_cost, contract_size_tensors
+from .paths.cotengrust import Cotengrust
+
+
+def communication_path_op_costs(inputs: Sequence[Tensor], path, tensor_cost: Sequence[float]):
+    """contraction_cost.rs:196-281 with only_count_ops = true: ((parallel, serial), memory)."""
+    def run(critical: bool):
+        ts = list(inputs)
+        cost = list(tensor_cost)
+        op, mem = 0.0, 0.0
+        if len(ts) == 1:
+            return cost[0], cost[0]
+        for (i, j) in path:
+            mem = max(mem, contract_size_tensors(ts[i], ts[j]))
+            c = contract_op_cost_tensors(ts[i], ts[j])
+            op = c + (max(cost[i], cost[j]) if critical else cost[i] + cost[j])
+            cost[i] = op
+            ts[i] = ts[i] ^ ts[j]
+        return op, mem
+    par, _ = run(True)
+    ser, mem = run(False)
+    return (par, ser), mem
+
+
+_local_cache: Dict[Tuple[int, ...], Tuple[List[Tuple[int, int]], float, Tuple[Tuple[int, ...], Tuple[int, ...]]]] = {}
+
+
+def _local(tn: Tensor, ids: Tuple[int, ...]):
+    """greedy local path (replace-left) + op cost + external legs of one partition; cached by content."""
+    hit = _local_cache.get(ids)
+    if hit is None:
+        comp = Tensor.new_composite([tn.tensors[i] for i in ids])
+        opt = Cotengrust(comp)
+        opt.find_path()
+        p = opt.get_best_replace_path()
+        cost, _ = contract_path_cost(comp.tensors, p, True)
+        ext = comp.external_tensor()
+        hit = (p.toplevel, cost, (tuple(ext.legs), tuple(ext.bond_dims)))
+        if len(_local_cache) > 200000:
+            _local_cache.clear()
+        _local_cache[ids] = hit
+    return hit
+
+
+def compute_solution(tn: Tensor, partitioning: Sequence[int]):
+    """repartitioning.rs:25-76 with CommunicationScheme::Greedy: returns
+    (partitioned_tn, path, parallel_cost, sum_cost)."""
+    ptn = partition_tensor_network(tn, partitioning)
+    ids_order: List[int] = []
+    for p in partitioning:
+        if p not in ids_order:
+            ids_order.append(p)
+    nested, costs, exts = {}, [], []
+    for k, pid in enumerate(ids_order):
+        ids = tuple(i for i, q in enumerate(partitioning) if q == pid)
+        top, cost, (el, ed) = _local(tn, ids)
+        nested[k] = ContractionPath.simple(top)
+        costs.append(cost)
+        exts.append(Tensor(list(el), list(ed)))
+    comm = Cotengrust(Tensor.new_composite(exts))
+    comm.find_path()
+    toplevel = comm.get_best_replace_path().toplevel
+    (par, ser), _ = communication_path_op_costs(exts, toplevel, costs)
+    return ptn, ContractionPath(nested, toplevel), par, ser
+
+
+def _trial_move(tn: Tensor, num_partitions: int, cur: List[int], rng) -> Optional[List[int]]:
+    trial = list(cur)
+    src = int(rng.integers(0, num_partitions))
+    members = [i for i, q in enumerate(trial) if q == src]
+    if len(members) < 3:
+        return None
+    dst = int(rng.integers(0, num_partitions - 1))
+    dst += dst >= src
+    if rng.random() < 0.25:
+        trial[members[int(rng.integers(0, len(members)))]] = dst
+        return trial
+    top, _, _ = _local(tn, tuple(members))
+    if len(top) < 2:
+        return None
+    pi = int(rng.integers(0, len(top) - 1))
+    leaves = {top[pi][0], top[pi][1]}
+    for (i, j) in reversed(top[:pi]):
+        if i in leaves:
+            leaves.add(j)
+    if len(leaves) >= len(members):
+        return None
+    for li in leaves:
+        trial[members[li]] = dst
+    return trial
+
+
+def balance_partitions(tn: Tensor, num_partitions: int, initial: Sequence[int], steps: int = 400, seed: int = 42,
+                       n_trials: int = 8, restart_iter: int = 50, t_start: float = 2.0, t_end: float = 0.05) -> Tuple[List[int], float]:
+    """Simulated annealing over partitionings (score = critical-path op cost of `compute_solution`).
+    Structure of simulated_annealing.rs:80-160: every iteration runs `n_trials` independent trial moves
+    from the current solution (each accepted with probability exp(-log2(score/current)/T)), continues
+    from the best of them, restarts from the best-so-far after `restart_iter` iterations without
+    improvement; T goes 2.0 -> 0.05 log-linearly over the *step budget* (`steps` evaluations).
+    Move model: the sub-tree below a random pair of a partition's local path moves to another
+    partition (intermediate-tensor model :251-352); with probability 1/4 a single tensor moves (:216-249)."""
+    rng = np.random.default_rng(seed)
+    cur = list(initial)
+    _, _, cur_score, _ = compute_solution(tn, cur)
+    best, best_score = list(cur), cur_score
+    iters = max(1, steps // n_trials)
+    last_improvement = 0
+    for it in range(iters):
+        temp = 2.0 ** (np.log2(t_start) + (np.log2(t_end) - np.log2(t_start)) * it / max(1, iters - 1))
+        cand, cand_score = None, None
+        for _ in range(n_trials):
+            t_sol, t_score = cur, cur_score
+            trial = _trial_move(tn, num_partitions, cur, rng)
+            if trial is not None:
+                _, _, score, _ = compute_solution(tn, trial)
+                if np.exp(-np.log2(score / cur_score) / temp) >= rng.random():
+                    t_sol, t_score = trial, score
+            if cand_score is None or t_score < cand_score:
+                cand, cand_score = t_sol, t_score
+        cur, cur_score = list(cand), cand_score
+        if cur_score < best_score:
+            best, best_score = list(cur), cur_score
+            last_improvement = 0
+        last_improvement += 1
+        if last_improvement == restart_iter:
+            cur, cur_score = list(best), best_score
+    return best, best_score
