@@ -354,8 +354,13 @@ def run_ours(args):
             S = slices_default
             int8_ops = 2.0 * 4 * (S * (S + 1) / 2) * M * N * K      # 4 real products per digit pair, S(S+1)/2 pairs
             ach = int8_ops / (kern_ms * 1e-3) * 1e-12
+            # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel on this workload
+            # (profiles/r01_ncu_oz_gemm_summary.txt, 8 slices): 23.445 GB + 2.144 GB per launch
+            traffic = 25.589e9 if S == 8 else None
             roofline = {"bound": "tensor", "kernel": "oz_gemm_kernel (tcgen05.mma.kind::i8, TMA, TMEM)", "achieved": ach,
-                        "peak": 2.0 * bf16_meas, "unit": "int8 TOP/s", "frac": ach / (2.0 * bf16_meas), "traffic": None,
+                        "peak": 2.0 * bf16_meas, "unit": "int8 TOP/s", "frac": ach / (2.0 * bf16_meas), "traffic": traffic,
+                        "traffic_note": "digit planes (640 MB) exceed the 126 MB L2, operand tiles are re-read per output tile; "
+                                        "algorithmic_bytes counts the FP64 operands/result once",
                         "peak_source": "2 x measured bf16 burst (MEASURED_PEAKS.json) as the int8 proxy; nominal dense int8 is 4500 TOP/s "
                                        f"(frac of nominal {ach / INT8_NOMINAL_TOPS:.3f})",
                         "kernel_ms": kern_ms, "executed_int8_ops": int8_ops, "slices": S,

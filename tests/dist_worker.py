@@ -70,7 +70,8 @@ def gpu_main():
     ctx = tb.Context(local)
     init_device_comm(ctx)
     q, r = int(os.environ.get("TNCB_Q", "20")), int(os.environ.get("TNCB_R", "8"))
-    tn, fpath, ptn, ppath = build_case(q, r, 5, world) if rank == 0 else (None, None, None, None)
+    seed = int(os.environ.get("TNCB_SEED", "5"))
+    tn, fpath, ptn, ppath = build_case(q, r, seed, world) if rank == 0 else (None, None, None, None)
     for it in range(3):
         dist.barrier(); ctx.synchronize()
         t0 = time.perf_counter()
