@@ -75,6 +75,9 @@ int tncb_ctx_reset_stats(tncb_ctx* ctx);
  * slices = 0 -> FP64 tensor pipe (DMMA) for every pair.  Smaller pairs always use DMMA / K0.
  * The environment variable TNCB_OZAKI_SLICES overrides the default. */
 int tncb_ctx_set_tcgen05_slices(tncb_ctx* ctx, int slices);
+/* Size thresholds of the tcgen05 engine (defaults: >= 96 output tiles of 128x128 and K >= 1536);
+ * (1, 256) routes every pair with M, N, K >= 256 to it (used by the parity tests). */
+int tncb_ctx_set_tcgen05_threshold(tncb_ctx* ctx, long long min_tiles, long long min_k);
 /* Measurement aid: bracket the dominant GEMM kernel of every large pair (k1_kernel / oz_gemm_kernel)
  * with CUDA events on the ctx stream; tncb_ctx_last_gemm_ms synchronises and returns the last one. */
 int tncb_ctx_time_gemm(tncb_ctx* ctx, int enable);

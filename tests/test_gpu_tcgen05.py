@@ -17,6 +17,7 @@ def tc_ctx(built_lib):
     import tnc_b200 as tb
     c = tb.Context(0)
     c.set_tcgen05_slices(8)
+    c.set_tcgen05_threshold(1, 256)     # route every pair with M, N, K >= 256 to the tcgen05 engine
     yield c
     c.close()
 
@@ -33,6 +34,25 @@ def check(ctx, rng, a_legs, a_dims, b_legs, b_dims, tol=1e-12, scale_rows=False)
     err = np.abs(got - ref).max()
     assert err <= tol * max(1.0, np.abs(ref).max()), err
     return got, ref
+
+
+def test_engine_is_really_tcgen05(tc_ctx):
+    """Guard against silently testing the DMMA path: the tcgen05 step launches 5 kernels
+    (2 exponent + 2 slicing + 1 GEMM) after the table build, the DMMA step 1 or 2."""
+    import tnc_b200 as tb
+    rng = np.random.default_rng(0)
+    a = tb.DeviceTensor.from_numpy(tc_ctx, rand_c(rng, (256, 256)))
+    b = tb.DeviceTensor.from_numpy(tc_ctx, rand_c(rng, (256, 256)))
+    c = tb.DeviceTensor.empty(tc_ctx, (256, 256))
+    tb.contract_pair_into(tc_ctx, [0, 1], a, [1, 2], b, c)     # builds the offset tables
+    tc_ctx.reset_stats()
+    tb.contract_pair_into(tc_ctx, [0, 1], a, [1, 2], b, c)
+    assert tc_ctx.stats()["kernel_launches"] == 5
+    tc_ctx.set_tcgen05_slices(0)
+    tc_ctx.reset_stats()
+    tb.contract_pair_into(tc_ctx, [0, 1], a, [1, 2], b, c)
+    assert tc_ctx.stats()["kernel_launches"] <= 2      # k1_kernel (+ split-K reduce)
+    tc_ctx.set_tcgen05_slices(8)
 
 
 def test_tcgen05_square(tc_ctx):

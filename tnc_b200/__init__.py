@@ -45,6 +45,9 @@ class Context:
         """0: FP64 tensor pipe (DMMA).  2..8: tcgen05 int8 digit slicing (K1') for large pairs."""
         check(self._l.tncb_ctx_set_tcgen05_slices(self.handle, int(slices)))
 
+    def set_tcgen05_threshold(self, min_tiles: int, min_k: int) -> None:
+        check(self._l.tncb_ctx_set_tcgen05_threshold(self.handle, int(min_tiles), int(min_k)))
+
     def time_gemm(self, enable: bool = True) -> None:
         check(self._l.tncb_ctx_time_gemm(self.handle, int(enable)))
 

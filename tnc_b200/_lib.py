@@ -59,6 +59,7 @@ SIGNATURES = {
     "tncb_ctx_stats": (C.c_int, [C.c_void_p, u64p, u64p, u64p]),
     "tncb_ctx_reset_stats": (C.c_int, [C.c_void_p]),
     "tncb_ctx_set_tcgen05_slices": (C.c_int, [C.c_void_p, C.c_int]),
+    "tncb_ctx_set_tcgen05_threshold": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong]),
     "tncb_ctx_time_gemm": (C.c_int, [C.c_void_p, C.c_int]),
     "tncb_ctx_last_gemm_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "tncb_tensor_upload": (C.c_int, [C.c_void_p, C.c_int, u64p, C.c_void_p, vpp]),

@@ -77,6 +77,7 @@ struct tncb_ctx {
   tncb::Arena arena;
   uint64_t launches = 0;
   int oz_slices = 8;  // 0 = DMMA only; 2..8 = tcgen05 int8 slicing (K1') for large pairs (8 = full mantissa)
+  long long oz_min_tiles = 96, oz_min_k = 1536;
   bool time_gemm = false; cudaEvent_t gemm_ev0 = nullptr, gemm_ev1 = nullptr; bool gemm_ev_valid = false;
   int sm_count = 148;
   // pinned staging for leaf uploads

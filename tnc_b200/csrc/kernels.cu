@@ -546,7 +546,7 @@ static int launch_k1(tncb_ctx* ctx, const PairPlan& P, const double2* A, const d
     const long long tiles = ((P.M + 127) / 128) * ((P.N + 127) / 128);
     // crossover measured on B200 (profiles/r01_engine_sweep.txt): short K is dominated by the S
     // FP64 read-modify-write flushes per tile, few tiles leave SMs idle (1 CTA per 128x128 tile)
-    if (force || (tiles >= 96 && P.K >= 1536) || (tiles >= 1024 && P.K >= 1024)) {
+    if (force || (tiles >= ctx->oz_min_tiles && P.K >= ctx->oz_min_k) || (tiles >= 1024 && P.K >= 1024)) {
       int rc = launch_k1_ozaki(ctx, P, A, B, C, ctx->oz_slices, a.offAm, a.offBn, a.offAk, a.offBk);
       if (rc != TNCB_ERR_OOM) return rc;   // no room for the digit planes: fall through to the DMMA engine
     }

@@ -334,6 +334,176 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant__
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
 }
 
+// ---- 2-CTA variant: tcgen05.mma.cta_group::2 (M = 256 over a CTA pair) ---------------------------
+// The 1-CTA kernel is bound by shared-memory bandwidth (profiles/r01_tcgen05_cluster_ab.txt): per
+// K-step it reads 24 KB of UMMA operands and takes 20 KB of TMA fills.  With cta_group::2 the pair
+// computes a 256 (n) x 128 (m) complex tile: every CTA supplies its own 128 Bt rows and only HALF of
+// the N = 256 operand (CTA0: Ar and nAi, CTA1: Ai and Ar), i.e. 16 KB reads + 16 KB fills per K-step,
+// and a stage shrinks from 80 KB to 64 KB (3 stages fit).  Protocol as in CUTLASS' 2-SM kernels: both
+// CTAs' TMA loads signal the leader's full barrier (peer bit cleared), only the leader issues the MMA,
+// commits are multicast to both CTAs, epilogues of both CTAs arrive on the leader's tmem-empty barrier.
+constexpr int OZ2_STAGES = 3;
+constexpr int OZ2_STAGE_BYTES = 4 * OZ_TILE;   // Br, Bi, X (Ar | Ai), Y (nAi | Ar)
+
+__device__ __forceinline__ void oz_tma_2d_2sm(const CUtensorMap* map, uint64_t* bar, void* smem, int c0, int c1) {
+  const uint32_t leader_bar = oz_smem(bar) & 0xFEFFFFFFu;   // Sm100MmaPeerBitMask: CTA0's barrier
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(oz_smem(smem)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void oz_umma_i8_2sm(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void oz_commit_2sm(uint64_t* bar) {   // arrives on `bar` in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(oz_smem(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void oz_mbar_arrive_cta(uint64_t* bar, uint32_t cta) {   // arrive on `bar` of cluster CTA `cta`
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(oz_smem(bar)), "r"(cta));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+oz_gemm2_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapA,
+                const __grid_constant__ OzArgs p) {
+  extern __shared__ __align__(1024) uint8_t oz_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(oz_smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full_bar[OZ2_STAGES], empty_bar[OZ2_STAGES], tfull_bar[2], tempty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ double col_scale[OZ_BT];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t crank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));   // cluster dims (2,1,1): rank = blockIdx.x & 1 (CTA pairs form along x)
+  const bool leader = crank == 0;
+  const int n0 = blockIdx.x * OZ_BT, m0 = blockIdx.y * OZ_BT;   // n on x so that a pair covers 256 Bt rows
+  const int S = p.S;
+  const int kb_per_chunk = OZ_KCHUNK / OZ_BKB;
+  const int nkc = (p.num_kb + kb_per_chunk - 1) / kb_per_chunk;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < OZ2_STAGES; s++) { oz_mbar_init(&full_bar[s], 1); oz_mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; b++) { oz_mbar_init(&tfull_bar[b], 1); oz_mbar_init(&tempty_bar[b], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < OZ_BT) {
+    const long long gm = (long long)m0 + threadIdx.x;
+    col_scale[threadIdx.x] = gm < p.M ? scalbn(1.0, p.exp_m[gm]) : 0.0;
+  }
+  if (warp == 1) {   // both CTAs, same warp id, same smem destination
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(oz_smem(&tmem_base_smem)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  oz_cluster_sync();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0 && lane == 0) {
+    // ================= TMA producer (both CTAs) =================
+    int it = 0;
+    for (int t = 0; t < S; t++)
+      for (int kc = 0; kc < nkc; kc++) {
+        const int kb0 = kc * kb_per_chunk, kb1 = min(p.num_kb, kb0 + kb_per_chunk);
+        for (int pp = 0; pp <= t; pp++) {
+          const int qq = t - pp;
+          for (int kb = kb0; kb < kb1; kb++, it++) {
+            const int s = it % OZ2_STAGES;
+            if (it >= OZ2_STAGES) oz_mbar_wait(&empty_bar[s], ((it / OZ2_STAGES) - 1) & 1);
+            uint8_t* st = smem + s * OZ2_STAGE_BYTES;
+            if (leader) oz_mbar_expect_tx(&full_bar[s], 2 * OZ2_STAGE_BYTES);   // bytes of both CTAs land on the leader's barrier
+            const int kx = kb * OZ_BKB;
+            oz_tma_2d_2sm(&mapB, &full_bar[s], st + 0 * OZ_TILE, kx, (0 * S + pp) * p.Np + n0);   // Br_p, own rows
+            oz_tma_2d_2sm(&mapB, &full_bar[s], st + 1 * OZ_TILE, kx, (1 * S + pp) * p.Np + n0);   // Bi_p
+            if (leader) {
+              oz_tma_2d_2sm(&mapA, &full_bar[s], st + 2 * OZ_TILE, kx, (1 * S + qq) * p.Mp + m0); // X: Ar  (N rows   0..127)
+              oz_tma_2d_2sm(&mapA, &full_bar[s], st + 3 * OZ_TILE, kx, (0 * S + qq) * p.Mp + m0); // Y: nAi
+            } else {
+              oz_tma_2d_2sm(&mapA, &full_bar[s], st + 2 * OZ_TILE, kx, (2 * S + qq) * p.Mp + m0); // X: Ai  (N rows 128..255)
+              oz_tma_2d_2sm(&mapA, &full_bar[s], st + 3 * OZ_TILE, kx, (1 * S + qq) * p.Mp + m0); // Y: Ar
+            }
+          }
+        }
+      }
+  } else if (warp == 1 && lane == 0 && leader) {
+    // ================= MMA issuer (leader CTA only) =================
+    // idesc: D=S32, A/B signed int8, K-major, N=256, M=256 (cta_group::2)
+    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
+    int it = 0, f = 0;
+    for (int t = 0; t < S; t++)
+      for (int kc = 0; kc < nkc; kc++, f++) {
+        const int buf = f & 1;
+        if (f >= 2) { oz_mbar_wait(&tempty_bar[buf], ((f >> 1) - 1) & 1); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+        const uint32_t acc = tmem_base + (uint32_t)(buf * 256);
+        const int kb0 = kc * kb_per_chunk, kb1 = min(p.num_kb, kb0 + kb_per_chunk);
+        bool first = true;
+        for (int pp = 0; pp <= t; pp++)
+          for (int kb = kb0; kb < kb1; kb++, it++) {
+            const int s = it % OZ2_STAGES;
+            oz_mbar_wait(&full_bar[s], (it / OZ2_STAGES) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint8_t* st = smem + s * OZ2_STAGE_BYTES;
+            const uint64_t d_br = oz_desc(st), d_bi = oz_desc(st + OZ_TILE), d_x = oz_desc(st + 2 * OZ_TILE), d_y = oz_desc(st + 3 * OZ_TILE);
+#pragma unroll
+            for (int k = 0; k < OZ_BKB / 32; k++) {
+              const uint64_t ko = (uint64_t)(k * 32 >> 4);
+              oz_umma_i8_2sm(acc, d_br + ko, d_x + ko, idesc, first ? 0u : 1u);   // Br x [Ar ; Ai]
+              first = false;
+              oz_umma_i8_2sm(acc, d_bi + ko, d_y + ko, idesc, 1u);               // Bi x [nAi ; Ar]
+            }
+            oz_commit_2sm(&empty_bar[s]);
+          }
+        oz_commit_2sm(&tfull_bar[buf]);
+      }
+  } else if (warp >= 2) {
+    // ================= epilogue (both CTAs; own 128 rows) =================
+    const int q = warp & 3;
+    const long long gn = (long long)n0 + q * 32 + lane;
+    const bool row_ok = gn < p.N;
+    const int en = row_ok ? p.exp_n[gn] : 0;
+    double2* crow = p.C + gn * p.M + m0;
+    int f = 0;
+    for (int t = 0; t < S; t++) {
+      const double rs = scalbn(1.0, en - 7 * (t + 2));
+      for (int kc = 0; kc < nkc; kc++, f++) {
+        const int buf = f & 1;
+        oz_mbar_wait(&tfull_bar[buf], (f >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256);
+#pragma unroll 1
+        for (int c0 = 0; c0 < OZ_BT; c0 += 32) {
+          uint32_t vr[32], vi[32];
+          oz_tmem_ld32(tbase + (uint32_t)c0, vr);
+          oz_tmem_ld32(tbase + (uint32_t)(128 + c0), vi);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+              const long long gm = (long long)m0 + c0 + j;
+              if (gm < p.M) {
+                const double sc = rs * col_scale[c0 + j];
+                double2 acc2 = make_double2((double)(int)vr[j] * sc, (double)(int)vi[j] * sc);
+                if (f != 0) { const double2 old = crow[c0 + j]; acc2.x += old.x; acc2.y += old.y; }
+                crow[c0 + j] = acc2;
+              }
+            }
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) oz_mbar_arrive_cta(&tempty_bar[buf], 0);   // the leader's MMA issuer waits for all 8 epilogue warps
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  oz_cluster_sync();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
 // ---- host side --------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -374,8 +544,11 @@ int launch_k1_ozaki(tncb_ctx* ctx, const PairPlan& P, const double2* A, const do
   // bound by shared-memory bandwidth (UMMA operand reads 24 KB + TMA writes 20 KB per K-step = 172 B/clk
   // against 128 B/clk), which multicast does not change; see profiles/r01_tcgen05_cluster_ab.txt.
   static const bool cl = std::getenv("TNCB_OZ_CLUSTER") != nullptr;
+  // default: the cta_group::2 kernel (oz_gemm2_kernel); TNCB_OZ_1CTA=1 selects the 1-CTA kernel
+  static const bool two_cta = std::getenv("TNCB_OZ_1CTA") == nullptr && !cl;
   const long long pad = cl ? 2 * OZ_BT : OZ_BT;   // 2x2 clusters need an even number of tiles per dimension
-  const long long Np = (P.N + pad - 1) / pad * pad, Mp = (P.M + pad - 1) / pad * pad;
+  const long long pad_n = two_cta ? 2 * OZ_BT : pad;                    // CTA pairs split 256 Bt rows
+  const long long Np = (P.N + pad_n - 1) / pad_n * pad_n, Mp = (P.M + pad - 1) / pad * pad;
   const long long Kp = (P.K + OZ_BKB - 1) / OZ_BKB * OZ_BKB;
   const size_t bytesB = (size_t)2 * S * Np * Kp, bytesA = (size_t)3 * S * Mp * Kp;
   const size_t bytesE = (size_t)(Np + Mp) * sizeof(int);
@@ -400,16 +573,35 @@ int launch_k1_ozaki(tncb_ctx* ctx, const PairPlan& P, const double2* A, const do
   }
   ctx->launches += 4;
   CUtensorMap mapB, mapA;
-  const uint32_t box_rows = cl ? OZ_BT / 2 : OZ_BT;
+  const uint32_t box_rows = (cl && !two_cta) ? OZ_BT / 2 : OZ_BT;
   if ((rc = make_map(&mapB, pb, (uint64_t)2 * S * Np, (uint64_t)Kp, box_rows)) || (rc = make_map(&mapA, pa, (uint64_t)3 * S * Mp, (uint64_t)Kp, box_rows))) { cleanup(); return rc; }
   OzArgs a;
   a.C = C; a.exp_n = exp_n; a.exp_m = exp_m; a.M = P.M; a.N = P.N; a.Np = (int)Np; a.Mp = (int)Mp;
   a.num_kb = (int)(Kp / OZ_BKB); a.S = S;
   const int smem_bytes = OZ_STAGES * OZ_STAGE_BYTES + 1024;
+  dim3 grid((unsigned)(Mp / OZ_BT), (unsigned)(Np / OZ_BT));
+  if (two_cta) {
+    const int smem2 = OZ2_STAGES * OZ2_STAGE_BYTES + 1024;
+    cudaError_t e2 = cudaFuncSetAttribute(oz_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+    if (e2 != cudaSuccess) { cleanup(); return fail(TNCB_ERR_CUDA, cudaGetErrorString(e2)); }
+    if (ctx->time_gemm) cudaEventRecord(ctx->gemm_ev0, st);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(Np / OZ_BT), (unsigned)(Mp / OZ_BT));   // n tiles on x
+    cfg.blockDim = dim3(OZ_THREADS); cfg.dynamicSmemBytes = smem2; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    e2 = cudaLaunchKernelEx(&cfg, oz_gemm2_kernel, mapB, mapA, a);
+    if (ctx->time_gemm) { cudaEventRecord(ctx->gemm_ev1, st); ctx->gemm_ev_valid = true; }
+    ctx->launches++;
+    cleanup();
+    if (e2 != cudaSuccess) return fail(TNCB_ERR_CUDA, std::string("2-CTA launch: ") + cudaGetErrorString(e2));
+    return TNCB_OK;
+  }
   auto kern = cl ? oz_gemm_kernel<true> : oz_gemm_kernel<false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   if (e != cudaSuccess) { cleanup(); return fail(TNCB_ERR_CUDA, cudaGetErrorString(e)); }
-  dim3 grid((unsigned)(Mp / OZ_BT), (unsigned)(Np / OZ_BT));
   if (ctx->time_gemm) cudaEventRecord(ctx->gemm_ev0, st);
   if (cl) {
     cudaLaunchConfig_t cfg{};

@@ -171,6 +171,12 @@ int tncb_ctx_set_tcgen05_slices(tncb_ctx* ctx, int slices) {
   return TNCB_OK;
 }
 
+int tncb_ctx_set_tcgen05_threshold(tncb_ctx* ctx, long long min_tiles, long long min_k) {
+  if (!ctx || min_tiles < 1 || min_k < 1) return fail(TNCB_ERR_INVALID, "bad argument");
+  ctx->oz_min_tiles = min_tiles; ctx->oz_min_k = min_k;
+  return TNCB_OK;
+}
+
 int tncb_ctx_time_gemm(tncb_ctx* ctx, int enable) {
   if (!ctx) return fail(TNCB_ERR_INVALID, "ctx is null");
   TNCB_CUDA(cudaSetDevice(ctx->device));
