@@ -177,6 +177,7 @@ struct OzArgs {
   int Np, Mp;         // padded plane rows
   int num_kb;         // Kp / 128
   int S;
+  int flags;          // bit 0: grouped tile raster (L2 reuse), bit 1: streaming (evict-first) accesses for the C read-modify-write
 };
 
 // CL = true: launched as 2x2 thread-block clusters.  The two CTAs of a cluster row work on the same
@@ -378,7 +379,20 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant_
   uint32_t crank;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));   // cluster dims (2,1,1): rank = blockIdx.x & 1 (CTA pairs form along x)
   const bool leader = crank == 0;
-  const int n0 = blockIdx.x * OZ_BT, m0 = blockIdx.y * OZ_BT;   // n on x so that a pair covers 256 Bt rows
+  int tile_n = blockIdx.x, tile_m = blockIdx.y;                // n on x so that a pair covers 256 Bt rows
+  if (p.flags & 1) {
+    // grouped raster: consecutive CTA pairs sweep bands of 8 n-pairs x all m-tiles, so that the ~74 pairs
+    // resident at a time share 8 Bt row-pairs and ~9 At tiles instead of all 16 row-pairs and ~5 At tiles
+    const int pairs_n = gridDim.x >> 1, tiles_m = gridDim.y, GROUP = 8;
+    const int L = (blockIdx.x >> 1) + pairs_n * blockIdx.y;    // linear pair id in launch order
+    const int per_band = GROUP * tiles_m;
+    const int band = L / per_band, first = band * GROUP;
+    const int gsize = min(GROUP, pairs_n - first);
+    const int r = L - band * per_band;
+    tile_n = ((first + r % gsize) << 1) | (blockIdx.x & 1);
+    tile_m = r / gsize;
+  }
+  const int n0 = tile_n * OZ_BT, m0 = tile_m * OZ_BT;
   const int S = p.S;
   const int kb_per_chunk = OZ_KCHUNK / OZ_BKB;
   const int nkc = (p.num_kb + kb_per_chunk - 1) / kb_per_chunk;
@@ -486,8 +500,13 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant_
               if (gm < p.M) {
                 const double sc = rs * col_scale[c0 + j];
                 double2 acc2 = make_double2((double)(int)vr[j] * sc, (double)(int)vi[j] * sc);
-                if (f != 0) { const double2 old = crow[c0 + j]; acc2.x += old.x; acc2.y += old.y; }
-                crow[c0 + j] = acc2;
+                if (p.flags & 2) {   // C is touched once per digit level: keep it out of the L2's way
+                  if (f != 0) { const double2 old = __ldcs(crow + c0 + j); acc2.x += old.x; acc2.y += old.y; }
+                  __stcs(crow + c0 + j, acc2);
+                } else {
+                  if (f != 0) { const double2 old = crow[c0 + j]; acc2.x += old.x; acc2.y += old.y; }
+                  crow[c0 + j] = acc2;
+                }
               }
             }
           }
@@ -578,6 +597,10 @@ int launch_k1_ozaki(tncb_ctx* ctx, const PairPlan& P, const double2* A, const do
   OzArgs a;
   a.C = C; a.exp_n = exp_n; a.exp_m = exp_m; a.M = P.M; a.N = P.N; a.Np = (int)Np; a.Mp = (int)Mp;
   a.num_kb = (int)(Kp / OZ_BKB); a.S = S;
+  // default 1 = grouped raster (A/B on C2, same box: GEMM 7.62 ms vs 8.14-8.26 ms; streaming C accesses, bit 1,
+  // measured slower: 9.04 ms) -- profiles/r01_tcgen05_cluster_ab.txt
+  static const int tune = std::getenv("TNCB_OZ_TUNE") ? atoi(std::getenv("TNCB_OZ_TUNE")) : 1;
+  a.flags = tune;
   const int smem_bytes = OZ_STAGES * OZ_STAGE_BYTES + 1024;
   dim3 grid((unsigned)(Mp / OZ_BT), (unsigned)(Np / OZ_BT));
   if (two_cta) {
