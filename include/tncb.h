@@ -69,15 +69,45 @@ void* tncb_ctx_stream(tncb_ctx* ctx);
 int tncb_ctx_stats(tncb_ctx* ctx, uint64_t* kernel_launches, uint64_t* arena_peak_bytes,
                    uint64_t* arena_live_bytes);
 int tncb_ctx_reset_stats(tncb_ctx* ctx);
-/* Dense-GEMM engine for large pairs (K >= 1536 and >= 96 output tiles of 128x128):
- * slices in [2,8] -> tcgen05 int8 path (exact 7-bit digit slicing; the default 8 slices cover the
- * full 53-bit mantissa, measured |err| ~ 1e-15..7e-15 of max|C|, like FP64 accumulation itself);
- * slices = 0 -> FP64 tensor pipe (DMMA) for every pair.  Smaller pairs always use DMMA / K0.
- * The environment variable TNCB_OZAKI_SLICES overrides the default. */
+/* Dense-GEMM engine for large GEMM-like pairs (M, N >= 128, K >= 256, M*N*K >= 2^28): K1', the tcgen05 int8
+ * tensor pipe (tcgen05.mma has no f64 kind).  Default engine = integer modular (CRT) emulation: every operand row
+ * is scaled by a power of two and truncated to an `a`-bit integer (a = 53 by default = the whole mantissa of the
+ * row's largest element), one int8 GEMM per coprime modulus (16 moduli for a = 53, K <= 2^13), exact CRT
+ * reconstruction.  GUARANTEED bound (not "exact"):
+ *     |C - C_exact|[n,m] <= 2^(4-a) * K * max|b[n,:]| * max|a[m,:]|     (max over real and imaginary parts)
+ * i.e. normwise per output row/column, FP64-GEMM-equivalent for a = 53 (measured 3e-16..1e-15 of max|C|).
+ * Elements far below their row maximum lose relative precision; a row whose maximum is below 2^-1000 keeps absolute
+ * accuracy 2^(-1000-a); a row containing NaN/Inf poisons its outputs with NaN.
+ * slices = 0 -> FP64 tensor pipe (DMMA) for every pair; non-zero -> K1' enabled (the value is the digit count of the
+ * legacy 7-bit digit-slicing engine, see tncb_ctx_set_tcgen05_engine).  Smaller pairs always use DMMA / K0 / K2.
+ * Environment: TNCB_OZAKI_SLICES, TNCB_TCGEN05_ENGINE, TNCB_CRT_MODULI override the defaults. */
 int tncb_ctx_set_tcgen05_slices(tncb_ctx* ctx, int slices);
-/* Size thresholds of the tcgen05 engine (defaults: >= 96 output tiles of 128x128 and K >= 1536);
- * (1, 256) routes every pair with M, N, K >= 256 to it (used by the parity tests). */
+/* 0 = modular / CRT engine (default), 1 = 7-bit digit slicing of round 1 (S(S+1)/2 int8 GEMMs, drops digit
+ * products p+q >= S: error <= (S+1) K 2^(-7S) of the same scale; kept for A/B measurements). */
+int tncb_ctx_set_tcgen05_engine(tncb_ctx* ctx, int engine);
+/* Requested normwise tolerance of K1': the engine keeps a = min(53, ceil(log2(16 K / rel))) bits per operand so that
+ * |C - C_exact|[n,m] <= rel * max|b[n,:]| * max|a[m,:]| holds for every pair; rel = 0 (default) = full mantissa.
+ * Fewer bits need fewer moduli (= int8 GEMM sweeps): see tncb_tcgen05_bound. */
+int tncb_ctx_set_tolerance(tncb_ctx* ctx, double rel);
+/* Pin the number of moduli (2..20; 0 = derive from the tolerance).  The operand bits then follow from
+ * log2(prod m_i) >= a + b + log2(K) + 3; measurement / test aid. */
+int tncb_ctx_set_tcgen05_moduli(tncb_ctx* ctx, int n_moduli);
+/* What K1' would do for contraction length k (no GPU): modulus count, operand bits and the guaranteed factor
+ * `bound` with |C - C_exact|[n,m] <= bound * max|b[n,:]| * max|a[m,:]|. */
+int tncb_tcgen05_bound(uint64_t k, double rel, int n_moduli_force, int* n_moduli, int* bits_a, int* bits_b, double* bound);
+/* The moduli and the split CRT weights rho_i = rho1_i + rho2_i = ((P/m_i)^-1 mod m_i) / m_i the engine uses for
+ * `n_moduli` moduli (host-only; arrays of n_moduli entries): C'/P = frac(sum_i y_i rho_i) for residues y_i. */
+int tncb_tcgen05_tables(int n_moduli, int* moduli, double* rho1, double* rho2, double* log2_product);
+/* Workspace budget of K1' (residue planes + residues, default 12 GiB): larger pairs are processed in panels. */
+int tncb_ctx_set_tcgen05_workspace(tncb_ctx* ctx, size_t bytes);
+/* Size thresholds: (min_tiles, min_k) of the digit-slicing engine; for the modular engine min_k is the K threshold
+ * and min_tiles == 1 drops the M*N*K >= 2^28 requirement (used by the parity tests). */
 int tncb_ctx_set_tcgen05_threshold(tncb_ctx* ctx, long long min_tiles, long long min_k);
+/* Pairs executed per engine since the last tncb_ctx_reset_stats: [0] K0, [1] K0 split-K, [2] K1 (DMMA),
+ * [3] K1 split-K, [4] K1' (tcgen05), [5] K2, [6] permute, [7] reserved. */
+int tncb_ctx_engine_counts(tncb_ctx* ctx, uint64_t counts[8]);
+/* int8 operations (2 x MAC) executed by the GEMM kernels of the last K1' pair and its modulus count. */
+int tncb_ctx_last_tcgen05_info(tncb_ctx* ctx, double* int8_ops, int* n_moduli);
 /* Measurement aid: bracket the dominant GEMM kernel of every large pair (k1_kernel / oz_gemm_kernel)
  * with CUDA events on the ctx stream; tncb_ctx_last_gemm_ms synchronises and returns the last one. */
 int tncb_ctx_time_gemm(tncb_ctx* ctx, int enable);
@@ -181,7 +211,10 @@ typedef struct tncb_path {
  * nested paths first (ascending child index), then the top-level pairs in order.
  * Leaves are materialised (gates.rs tables) and uploaded in ONE host->device
  * copy, every pair runs on the device without host round trips, and the result
- * stays on the device.  out_legs must have room for *n_out legs (<= 64). */
+ * stays on the device.  out_legs must have room for *n_out legs (<= 64).
+ * TNCB_DATA_DEVICE leaves are consumed atomically: on TNCB_OK every one of them has been freed
+ * (the Rust call moves them); on ANY error none has been touched and the caller still owns all of
+ * them.  Their storage stays allocated until the whole schedule has been enqueued. */
 int tncb_contract_tensor_network(tncb_ctx* ctx, const tncb_tn* tn, const tncb_path* path,
                                  tncb_tensor** out, int* n_out, uint64_t* out_legs);
 
@@ -189,6 +222,10 @@ int tncb_contract_tensor_network(tncb_ctx* ctx, const tncb_tn* tn, const tncb_pa
  * (e.g. other bitstrings or angles) re-uses the schedule, arena layout and the
  * captured CUDA graph. */
 int tncb_plan_create(tncb_ctx* ctx, const tncb_tn* tn, const tncb_path* path, tncb_plan** out);
+/* `tn` must have the structure the plan was compiled from: every leaf is re-validated (kind, rank,
+ * dims, non-null payload, live device handle) -> TNCB_ERR_INVALID / TNCB_ERR_SHAPE /
+ * TNCB_ERR_UNCONTRACTED before any copy.  Device leaves: same atomic rule as above.  A plan may be
+ * destroyed before or after its context. */
 int tncb_plan_execute(tncb_ctx* ctx, tncb_plan* plan, const tncb_tn* tn,
                       tncb_tensor** out, int* n_out, uint64_t* out_legs);
 /* Schedule facts: #pairs, sum 8MNK, sum 16(MK+KN+MN), peak arena bytes, #kernels. */
@@ -210,7 +247,10 @@ int tncb_comm_allreduce_sum(tncb_ctx* ctx, tncb_tensor* t);
 int tncb_comm_destroy(tncb_ctx* ctx);
 /* get_tensor_mapping (mpi/communication.rs:89-115): partition -> rank, the
  * partition on the left of the last top-level pair goes to rank 0, the others
- * to 1, 2, ... in ascending partition index.  rank_of[p] for p < n_partitions. */
+ * to 1, 2, ... in the order the reference walks `path.nested.keys()`: the
+ * iteration order of FxHashMap<usize,_>::from_iter(partition_index) (rustc-hash
+ * 2.1.1 on hashbrown), reproduced bit-exactly and pinned by the reference KAT
+ * communication.rs:257-279 (0 -> 0, 1 -> 2, 2 -> 1).  rank_of[p] for p < n_partitions. */
 int tncb_fanin_mapping(size_t n_partitions, const uint64_t* partition_index,
                        size_t n_pairs, const uint64_t* toplevel_pairs, int world_size,
                        int* rank_of_partition);

@@ -122,8 +122,8 @@ def test_fanin_mapping_kat(built_lib):
     ranks = (C.c_int * 3)()
     rc = built_lib.tncb_fanin_mapping(3, u64_array([0, 1, 2]), 2, u64_array([0, 2, 0, 1]), 4, ranks)
     assert rc == 0
-    # final tensor (left of the last pair) = 0 -> rank 0; others 1, 2 in ascending order
-    assert list(ranks) == [0, 1, 2]
+    # the reference's assertions verbatim: rank(0) == 0, rank(1) == 2, rank(2) == 1 (FxHashMap walk order 0, 2, 1)
+    assert list(ranks) == [0, 2, 1]
     rc = built_lib.tncb_fanin_mapping(3, u64_array([0, 1, 2]), 2, u64_array([1, 0, 2, 1]), 4, ranks)
     assert rc == 0 and list(ranks) == [1, 2, 0]
     rc = built_lib.tncb_fanin_mapping(3, u64_array([0, 1, 2]), 2, u64_array([0, 2, 0, 1]), 2, ranks)

@@ -37,3 +37,20 @@ def test_compute_solution_and_sa_are_deterministic_and_monotone():
     assert best1 == best2 and s1 == s2                 # step budget + seed -> reproducible
     assert s1 <= par                                   # never worse than the start
     assert compute_solution(tn, best1)[2] == s1
+
+
+def test_two_networks_back_to_back_do_not_share_a_cache():
+    """the local-path cache was a module global keyed by child indices only, so a second network
+    was scored with the first one's legs.  Scores must equal a fresh evaluation regardless of call history."""
+    tn1 = random_circuit(10, 5, 0.5, 0.5, np.random.default_rng(1))
+    tn2 = random_circuit(10, 7, 0.5, 0.5, np.random.default_rng(2))
+    n = min(len(tn1.tensors), len(tn2.tensors))
+    part = [i % 2 for i in range(n)]
+    p1 = part + [0] * (len(tn1.tensors) - n)
+    p2 = part + [0] * (len(tn2.tensors) - n)
+    alone2 = compute_solution(tn2, p2)[2:]
+    compute_solution(tn1, p1)
+    b1, s1 = balance_partitions(tn1, 2, p1, steps=40, seed=3)
+    assert compute_solution(tn2, p2)[2:] == alone2
+    b2, s2 = balance_partitions(tn2, 2, p2, steps=40, seed=3)
+    assert compute_solution(tn2, b2)[2] == s2 and compute_solution(tn1, b1)[2] == s1

@@ -45,6 +45,31 @@ class Context:
         """0: FP64 tensor pipe (DMMA).  2..8: tcgen05 int8 digit slicing (K1') for large pairs."""
         check(self._l.tncb_ctx_set_tcgen05_slices(self.handle, int(slices)))
 
+    def set_tcgen05_engine(self, engine: int) -> None:
+        """0: modular (CRT) int8 engine (default).  1: the 7-bit digit-slicing engine of round 1."""
+        check(self._l.tncb_ctx_set_tcgen05_engine(self.handle, int(engine)))
+
+    def set_tolerance(self, rel: float) -> None:
+        """Normwise tolerance of K1' (0 = full FP64 mantissa), see tncb.h."""
+        check(self._l.tncb_ctx_set_tolerance(self.handle, float(rel)))
+
+    def set_tcgen05_moduli(self, n: int) -> None:
+        check(self._l.tncb_ctx_set_tcgen05_moduli(self.handle, int(n)))
+
+    def set_tcgen05_workspace(self, nbytes: int) -> None:
+        check(self._l.tncb_ctx_set_tcgen05_workspace(self.handle, int(nbytes)))
+
+    def engine_counts(self) -> dict:
+        arr = (C.c_uint64 * 8)()
+        check(self._l.tncb_ctx_engine_counts(self.handle, arr))
+        names = ["k0", "k0_splitk", "k1_dmma", "k1_dmma_splitk", "k1_tcgen05", "k2", "permute", "reserved"]
+        return {n: int(arr[i]) for i, n in enumerate(names)}
+
+    def last_tcgen05_info(self) -> dict:
+        ops, n = C.c_double(), C.c_int()
+        check(self._l.tncb_ctx_last_tcgen05_info(self.handle, C.byref(ops), C.byref(n)))
+        return {"int8_ops": ops.value, "n_moduli": n.value}
+
     def set_tcgen05_threshold(self, min_tiles: int, min_k: int) -> None:
         check(self._l.tncb_ctx_set_tcgen05_threshold(self.handle, int(min_tiles), int(min_k)))
 
@@ -135,6 +160,22 @@ class DeviceTensor:
             self.free()
         except Exception:
             pass
+
+
+def tcgen05_bound(k: int, rel: float = 0.0, n_moduli: int = 0) -> dict:
+    """Host-only: what K1' does for contraction length k (tncb_tcgen05_bound)."""
+    n, a, b, bd = C.c_int(), C.c_int(), C.c_int(), C.c_double()
+    check(lib().tncb_tcgen05_bound(int(k), float(rel), int(n_moduli), C.byref(n), C.byref(a), C.byref(b), C.byref(bd)))
+    return {"n_moduli": n.value, "bits_a": a.value, "bits_b": b.value, "bound": bd.value}
+
+
+def tcgen05_tables(n_moduli: int) -> dict:
+    """Host-only: moduli and split CRT weights of K1' (tncb_tcgen05_tables)."""
+    m = (C.c_int * n_moduli)()
+    r1, r2 = (C.c_double * n_moduli)(), (C.c_double * n_moduli)()
+    lp = C.c_double()
+    check(lib().tncb_tcgen05_tables(int(n_moduli), m, r1, r2, C.byref(lp)))
+    return {"moduli": list(m), "rho1": list(r1), "rho2": list(r2), "log2_product": lp.value}
 
 
 def contract_pair(ctx: Context, a_legs, a, b_legs, b):

@@ -59,6 +59,14 @@ SIGNATURES = {
     "tncb_ctx_stats": (C.c_int, [C.c_void_p, u64p, u64p, u64p]),
     "tncb_ctx_reset_stats": (C.c_int, [C.c_void_p]),
     "tncb_ctx_set_tcgen05_slices": (C.c_int, [C.c_void_p, C.c_int]),
+    "tncb_ctx_set_tcgen05_engine": (C.c_int, [C.c_void_p, C.c_int]),
+    "tncb_ctx_set_tolerance": (C.c_int, [C.c_void_p, C.c_double]),
+    "tncb_ctx_set_tcgen05_moduli": (C.c_int, [C.c_void_p, C.c_int]),
+    "tncb_tcgen05_bound": (C.c_int, [C.c_uint64, C.c_double, C.c_int, i32p, i32p, i32p, f64p]),
+    "tncb_tcgen05_tables": (C.c_int, [C.c_int, i32p, f64p, f64p, f64p]),
+    "tncb_ctx_set_tcgen05_workspace": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "tncb_ctx_engine_counts": (C.c_int, [C.c_void_p, u64p]),
+    "tncb_ctx_last_tcgen05_info": (C.c_int, [C.c_void_p, f64p, i32p]),
     "tncb_ctx_set_tcgen05_threshold": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong]),
     "tncb_ctx_time_gemm": (C.c_int, [C.c_void_p, C.c_int]),
     "tncb_ctx_last_gemm_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),

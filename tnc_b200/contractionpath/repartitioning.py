@@ -16,36 +16,25 @@ import numpy as np
 from ..tensornetwork.partitioning import partition_tensor_network
 from ..tensornetwork.tensor import Tensor
 from . import ContractionPath
-from .contraction_cost import contract_op_cost_tensors, contract_path_cost, contract_size_tensors
+from . import contraction_cost as _cc
+from .contraction_cost import contract_path_cost
 from .paths.cotengrust import Cotengrust
 
 
 def communication_path_op_costs(inputs: Sequence[Tensor], path, tensor_cost: Sequence[float]):
-    """contraction_cost.rs:196-281 with only_count_ops = true: ((parallel, serial), memory)."""
-    def run(critical: bool):
-        ts = list(inputs)
-        cost = list(tensor_cost)
-        op, mem = 0.0, 0.0
-        if len(ts) == 1:
-            return cost[0], cost[0]
-        for (i, j) in path:
-            mem = max(mem, contract_size_tensors(ts[i], ts[j]))
-            c = contract_op_cost_tensors(ts[i], ts[j])
-            op = c + (max(cost[i], cost[j]) if critical else cost[i] + cost[j])
-            cost[i] = op
-            ts[i] = ts[i] ^ ts[j]
-        return op, mem
-    par, _ = run(True)
-    ser, mem = run(False)
-    return (par, ser), mem
+    """contraction_cost.rs:196-208 with only_count_ops = true: ((parallel, serial), memory)."""
+    return _cc.communication_path_op_costs(inputs, path, True, tensor_cost)
 
 
-_local_cache: Dict[Tuple[int, ...], Tuple[List[Tuple[int, int]], float, Tuple[Tuple[int, ...], Tuple[int, ...]]]] = {}
+LocalCache = Dict[Tuple, Tuple[List[Tuple[int, int]], float, Tuple[Tuple[int, ...], Tuple[int, ...]]]]
 
 
-def _local(tn: Tensor, ids: Tuple[int, ...]):
-    """greedy local path (replace-left) + op cost + external legs of one partition; cached by content."""
-    hit = _local_cache.get(ids)
+def _local(tn: Tensor, ids: Tuple[int, ...], cache: Optional[LocalCache]):
+    """greedy local path (replace-left) + op cost + external legs of one partition.  `cache` belongs to ONE
+    call of compute_solution / balance_partitions (i.e. one network); its key also carries the members'
+    legs and dims so that a cache can never answer for another network's tensors."""
+    key = (ids, tuple((tuple(tn.tensors[i].legs), tuple(tn.tensors[i].bond_dims)) for i in ids))
+    hit = cache.get(key) if cache is not None else None
     if hit is None:
         comp = Tensor.new_composite([tn.tensors[i] for i in ids])
         opt = Cotengrust(comp)
@@ -54,13 +43,12 @@ def _local(tn: Tensor, ids: Tuple[int, ...]):
         cost, _ = contract_path_cost(comp.tensors, p, True)
         ext = comp.external_tensor()
         hit = (p.toplevel, cost, (tuple(ext.legs), tuple(ext.bond_dims)))
-        if len(_local_cache) > 200000:
-            _local_cache.clear()
-        _local_cache[ids] = hit
+        if cache is not None:
+            cache[key] = hit
     return hit
 
 
-def compute_solution(tn: Tensor, partitioning: Sequence[int]):
+def compute_solution(tn: Tensor, partitioning: Sequence[int], cache: Optional[LocalCache] = None):
     """repartitioning.rs:25-76 with CommunicationScheme::Greedy: returns
     (partitioned_tn, path, parallel_cost, sum_cost)."""
     ptn = partition_tensor_network(tn, partitioning)
@@ -71,7 +59,7 @@ def compute_solution(tn: Tensor, partitioning: Sequence[int]):
     nested, costs, exts = {}, [], []
     for k, pid in enumerate(ids_order):
         ids = tuple(i for i, q in enumerate(partitioning) if q == pid)
-        top, cost, (el, ed) = _local(tn, ids)
+        top, cost, (el, ed) = _local(tn, ids, cache)
         nested[k] = ContractionPath.simple(top)
         costs.append(cost)
         exts.append(Tensor(list(el), list(ed)))
@@ -82,7 +70,7 @@ def compute_solution(tn: Tensor, partitioning: Sequence[int]):
     return ptn, ContractionPath(nested, toplevel), par, ser
 
 
-def _trial_move(tn: Tensor, num_partitions: int, cur: List[int], rng) -> Optional[List[int]]:
+def _trial_move(tn: Tensor, num_partitions: int, cur: List[int], rng, cache: Optional[LocalCache] = None) -> Optional[List[int]]:
     trial = list(cur)
     src = int(rng.integers(0, num_partitions))
     members = [i for i, q in enumerate(trial) if q == src]
@@ -93,7 +81,7 @@ def _trial_move(tn: Tensor, num_partitions: int, cur: List[int], rng) -> Optiona
     if rng.random() < 0.25:
         trial[members[int(rng.integers(0, len(members)))]] = dst
         return trial
-    top, _, _ = _local(tn, tuple(members))
+    top, _, _ = _local(tn, tuple(members), cache)
     if len(top) < 2:
         return None
     pi = int(rng.integers(0, len(top) - 1))
@@ -118,8 +106,9 @@ def balance_partitions(tn: Tensor, num_partitions: int, initial: Sequence[int], 
     Move model: the sub-tree below a random pair of a partition's local path moves to another
     partition (intermediate-tensor model :251-352); with probability 1/4 a single tensor moves (:216-249)."""
     rng = np.random.default_rng(seed)
+    cache: LocalCache = {}                     # per call: never shared between networks
     cur = list(initial)
-    _, _, cur_score, _ = compute_solution(tn, cur)
+    _, _, cur_score, _ = compute_solution(tn, cur, cache)
     best, best_score = list(cur), cur_score
     iters = max(1, steps // n_trials)
     last_improvement = 0
@@ -128,9 +117,9 @@ def balance_partitions(tn: Tensor, num_partitions: int, initial: Sequence[int], 
         cand, cand_score = None, None
         for _ in range(n_trials):
             t_sol, t_score = cur, cur_score
-            trial = _trial_move(tn, num_partitions, cur, rng)
+            trial = _trial_move(tn, num_partitions, cur, rng, cache)
             if trial is not None:
-                _, _, score, _ = compute_solution(tn, trial)
+                _, _, score, _ = compute_solution(tn, trial, cache)
                 if np.exp(-np.log2(score / cur_score) / temp) >= rng.random():
                     t_sol, t_score = trial, score
             if cand_score is None or t_score < cand_score:

@@ -104,11 +104,17 @@ class SlicedNetwork:
 
     def __init__(self, tn: Tensor, legs: Sequence[int]):
         self.tn, self.legs = tn, list(legs)
-        self.leaves = _flat(tn)
+        self.leaves = list(_flat(tn))
         self.touched = {}
         for idx, t in enumerate(self.leaves):
             if any(l in t.legs for l in self.legs):
                 self.touched[idx] = _leaf_array(t)
+            elif t.tensordata.kind == "matrix" and not isinstance(t.tensordata.matrix, np.ndarray):
+                # a device-resident leaf shared by every slice would be consumed by the first one:
+                # download it once, every slice then uploads its own copy with the leaf block
+                nt = Tensor(t.legs, t.bond_dims)
+                nt.set_tensor_data(TensorData.Matrix(_leaf_array(t)))
+                self.leaves[idx] = nt
         self.assignments = slice_assignments(tn, self.legs)
 
     def slice(self, assignment: Sequence[int]) -> Tensor:

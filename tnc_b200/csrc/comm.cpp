@@ -138,8 +138,45 @@ int tncb_comm_destroy(tncb_ctx* ctx) {
   return TNCB_OK;
 }
 
-// get_tensor_mapping (mpi/communication.rs:89-115).  The reference iterates an FxHashMap
-// (unspecified order); ascending partition index is used here and documented.
+// Iteration order of `FxHashMap<usize, _>::from_iter(keys)` as the reference builds `path.nested`
+// (contractionpath.rs:40-47): rustc-hash 2.1.1 (hash = rotl((0 + key) * 0xf1357aea2e62a9c5, 26), tnc/Cargo.toml:32)
+// on hashbrown's SwissTable (Cargo.lock): buckets = capacity_to_buckets(n), a key goes to the first EMPTY
+// control byte of the 16-wide group probe starting at hash & mask (triangular stride; tables smaller than a
+// group rescan from 0 when the hit lands in the mirror bytes), and iteration walks the buckets in ascending
+// index.  Restated from the published crates (both absent from /root/reference); pinned by the reference's
+// own KAT communication.rs:257-279 (keys 0,1,2 iterate as 0,2,1).
+static std::vector<size_t> fxhashmap_iteration_order(const uint64_t* keys, size_t n) {
+  size_t buckets = n < 4 ? 4 : (n < 8 ? 8 : 1);
+  if (n >= 8) { size_t adj = n * 8 / 7; while (buckets < adj) buckets <<= 1; }
+  const size_t mask = buckets - 1, W = 16;
+  std::vector<char> full(buckets, 0);
+  std::vector<size_t> owner(buckets, 0);
+  for (size_t q = 0; q < n; q++) {
+    const uint64_t m = keys[q] * 0xf1357aea2e62a9c5ull;
+    const uint64_t h = (m << 26) | (m >> 38);
+    size_t pos = (size_t)h & mask, stride = 0, slot = buckets;
+    while (slot == buckets) {
+      for (size_t b = 0; b < W && slot == buckets; b++) {
+        const size_t i = pos + b;           // control bytes [buckets, buckets+W) mirror the start (or are EMPTY)
+        if (i < buckets) { if (!full[i]) slot = i; }
+        else if (buckets < W) {             // small table: bytes buckets..W-1 are always EMPTY -> masked index, then the fix-up
+          size_t idx = i & mask;
+          if (full[idx]) { idx = 0; while (full[idx]) idx++; }
+          slot = idx;
+        } else if (!full[i & mask]) slot = i & mask;
+      }
+      stride += W; pos = (pos + stride) & mask;
+    }
+    full[slot] = 1; owner[slot] = q;
+  }
+  std::vector<size_t> order;
+  for (size_t i = 0; i < buckets; i++) if (full[i]) order.push_back(owner[i]);
+  return order;
+}
+
+// get_tensor_mapping (mpi/communication.rs:89-115): walk `path.nested.keys()` (FxHashMap order, see above;
+// `partition_index` is the insertion order, ascending in every caller here and in the reference's finders),
+// the partition on the left of the last top-level pair gets rank 0, the others 1, 2, ... in walk order.
 int tncb_fanin_mapping(size_t n_partitions, const uint64_t* partition_index, size_t n_pairs,
                        const uint64_t* toplevel_pairs, int world_size, int* rank_of_partition) {
   if ((n_partitions && (!partition_index || !rank_of_partition)) || (n_pairs && !toplevel_pairs))
@@ -149,11 +186,8 @@ int tncb_fanin_mapping(size_t n_partitions, const uint64_t* partition_index, siz
     return TNCB_OK;
   }
   const uint64_t final_tensor = toplevel_pairs[2 * (n_pairs - 1)];
-  std::vector<size_t> order(n_partitions);
-  for (size_t p = 0; p < n_partitions; p++) order[p] = p;
-  std::sort(order.begin(), order.end(), [&](size_t x, size_t y) { return partition_index[x] < partition_index[y]; });
   int used = 1;
-  for (size_t q : order) {
+  for (size_t q : fxhashmap_iteration_order(partition_index, n_partitions)) {
     if (partition_index[q] == final_tensor) rank_of_partition[q] = 0;
     else rank_of_partition[q] = used++;
   }

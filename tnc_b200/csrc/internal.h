@@ -76,8 +76,15 @@ struct tncb_ctx {
   cudaStream_t stream = nullptr;
   tncb::Arena arena;
   uint64_t launches = 0;
-  int oz_slices = 8;  // 0 = DMMA only; 2..8 = tcgen05 int8 slicing (K1') for large pairs (8 = full mantissa)
-  long long oz_min_tiles = 96, oz_min_k = 1536;
+  int oz_slices = 8;  // 0 = DMMA only; otherwise the tcgen05 int8 engine (K1') takes large pairs (digit-slicing engine: #slices)
+  int oz_engine = 0;  // 0 = CRT / modular engine (crt.cu, default), 1 = 7-bit digit slicing (ozaki.cu, kept for A/B)
+  long long oz_min_tiles = 96, oz_min_k = 1536;   // thresholds of the digit-slicing engine
+  // CRT engine: operand bits (53 = full mantissa) or a requested tolerance, forced modulus count, thresholds, workspace
+  int crt_bits = 53; double crt_tol = 0.0; int crt_nmod_force = 0;
+  long long crt_min_k = 256; double crt_min_mnk = 268435456.0;   // K >= 256 and M*N*K >= 2^28
+  size_t crt_ws_bytes = (size_t)12 << 30; int crt_group = 8;
+  double last_int8_ops = 0.0; int last_nmod = 0;
+  uint64_t engine_count[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // K0, K0 split-K, K1 DMMA, K1 DMMA split-K, K1' tcgen05, K2, permute, -
   bool time_gemm = false; cudaEvent_t gemm_ev0 = nullptr, gemm_ev1 = nullptr; bool gemm_ev_valid = false;
   int sm_count = 148;
   // pinned staging for leaf uploads
@@ -92,7 +99,11 @@ struct tncb_ctx {
   double2* partial_override = nullptr; size_t partial_override_elems = 0;  // set while a plan graph is captured
   // NCCL
   void* nccl_comm = nullptr; int world = 1, rank = 0;
+  // plans that hold device state (graph, workspace) on this context; detached by tncb_ctx_destroy
+  std::vector<struct tncb_plan*> plans;
 };
+
+extern "C" void tncb_plan_release_device_state(struct tncb_plan* plan);
 
 namespace tncb {
 // ---- kernel launchers (kernels.cu) ---------------------------------------------------
@@ -105,6 +116,13 @@ int ensure_tab(tncb_ctx* ctx, size_t elems);
 // K1': tcgen05 int8-sliced ZGEMM (ozaki.cu); tables as built by launch_k1
 int launch_k1_ozaki(tncb_ctx* ctx, const PairPlan& p, const double2* A, const double2* B, double2* C, int S,
                     const long long* offAm, const long long* offBn, const long long* offAk, const long long* offBk);
+
+// K1' default engine: tcgen05 int8 GEMMs over coprime moduli + CRT reconstruction (crt.cu)
+int launch_k1_crt(tncb_ctx* ctx, const PairPlan& p, const double2* A, const double2* B, double2* C,
+                  const long long* offAm, const long long* offBn, const long long* offAk, const long long* offBk);
+void crt_choose(long long K, int want_bits, int nmod_force, int* nmod, int* bits_a, int* bits_b);
+int crt_bits_for_tolerance(long long K, double tol);
+int crt_export_tables(int nmod, int* moduli, double* rho1, double* rho2, double* log2_product);
 
 int ensure_partial(tncb_ctx* ctx, size_t elems);
 size_t k0_partial_elems(int sm_count, const PairPlan& p);

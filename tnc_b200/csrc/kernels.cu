@@ -458,6 +458,7 @@ static int launch_k0(tncb_ctx* ctx, const PairPlan& P, const double2* A, const d
     default: launch_k0_g<32>(grid, ctx->stream, A, B, dst, a); break;
   }
   ctx->launches++;
+  ctx->engine_count[ksplit > 1 ? 1 : 0]++;
   if (ksplit > 1) {
     reduce_partials_kernel<<<(unsigned)((MN + 255) / 256), 256, 0, ctx->stream>>>(dst, C, MN, (int)ksplit);
     ctx->launches++;
@@ -511,6 +512,7 @@ static int launch_k1_modes(tncb_ctx* ctx, K1Args& a, bool bkf, bool akf, bool al
   else if (!bkf && akf) rc = launch_k1_cfg<BN, BM, WN, WM, ST, false, true, MINB>(ctx, a);
   else rc = launch_k1_cfg<BN, BM, WN, WM, ST, false, false, MINB>(ctx, a);
   if (rc) return rc;
+  ctx->engine_count[a.ksplit > 1 ? 3 : 2]++;
   if (a.ksplit > 1) {
     const long long MN = a.M * a.N;
     reduce_partials_kernel<<<(unsigned)((MN + 255) / 256), 256, 0, ctx->stream>>>(ctx->partial, final_c, MN, a.ksplit);
@@ -540,15 +542,25 @@ static int launch_k1(tncb_ctx* ctx, const PairPlan& P, const double2* A, const d
   a.A = A; a.B = B; a.C = C;
   a.offAm = ctx->tab; a.offBn = ctx->tab + P.M; a.offAk = ctx->tab + P.M + P.N; a.offBk = a.offAk + P.K;
   a.M = P.M; a.N = P.N; a.K = P.K;
-  // K1': the same contraction on tcgen05 (exact int8 slicing, ozaki.cu) for large GEMM-like pairs
-  if (ctx->oz_slices > 0 && P.M >= 256 && P.N >= 256 && P.K >= 256) {
+  // K1': the same contraction on the tcgen05 int8 pipe for large GEMM-like pairs.  Default engine: modular
+  // (CRT) emulation, crt.cu; the 7-bit digit-slicing engine of round 1 (ozaki.cu) stays selectable for A/B.
+  if (ctx->oz_slices > 0 && P.M >= 128 && P.N >= 128) {
     static const bool force = std::getenv("TNCB_FORCE_TCGEN05") != nullptr;  // tuning aid: skip the size heuristic
-    const long long tiles = ((P.M + 127) / 128) * ((P.N + 127) / 128);
-    // crossover measured on B200 (profiles/r01_engine_sweep.txt): short K is dominated by the S
-    // FP64 read-modify-write flushes per tile, few tiles leave SMs idle (1 CTA per 128x128 tile)
-    if (force || (tiles >= ctx->oz_min_tiles && P.K >= ctx->oz_min_k) || (tiles >= 1024 && P.K >= 1024)) {
-      int rc = launch_k1_ozaki(ctx, P, A, B, C, ctx->oz_slices, a.offAm, a.offBn, a.offAk, a.offBk);
-      if (rc != TNCB_ERR_OOM) return rc;   // no room for the digit planes: fall through to the DMMA engine
+    if (ctx->oz_engine == 0) {
+      const double mnk = (double)P.M * (double)P.N * (double)P.K;
+      if (force || (P.K >= ctx->crt_min_k && mnk >= ctx->crt_min_mnk)) {
+        int rc = launch_k1_crt(ctx, P, A, B, C, a.offAm, a.offBn, a.offAk, a.offBk);
+        if (rc != TNCB_ERR_OOM && rc != TNCB_ERR_UNSUPPORTED) return rc;   // no room for the residue planes: DMMA engine
+      }
+    } else if (P.M >= 256 && P.N >= 256 && P.K >= 256) {
+      const long long tiles = ((P.M + 127) / 128) * ((P.N + 127) / 128);
+      // crossover measured on B200 (profiles/r01_engine_sweep.txt): short K is dominated by the S
+      // FP64 read-modify-write flushes per tile, few tiles leave SMs idle (1 CTA per 128x128 tile)
+      if (force || (tiles >= ctx->oz_min_tiles && P.K >= ctx->oz_min_k) || (tiles >= 1024 && P.K >= 1024)) {
+        int rc = launch_k1_ozaki(ctx, P, A, B, C, ctx->oz_slices, a.offAm, a.offBn, a.offAk, a.offBk);
+        if (rc == TNCB_OK) ctx->engine_count[4]++;
+        if (rc != TNCB_ERR_OOM) return rc;   // no room for the digit planes: fall through to the DMMA engine
+      }
     }
   }
   // Tile choice (A/B-measured on B200, C2 pair, profiles/r01_k1_tile_ab.txt): 64x64 tiles with a
@@ -662,6 +674,7 @@ static int launch_k2(tncb_ctx* ctx, const PairPlan& P, const double2* A, const d
     default: k2_kernel<16><<<blocks, 256, 0, ctx->stream>>>(Big, Sml, C, a); break;
   }
   ctx->launches++;
+  ctx->engine_count[5]++;
   TNCB_CUDA(cudaGetLastError());
   return TNCB_OK;
 }
@@ -693,6 +706,7 @@ int launch_permute(tncb_ctx* ctx, const double2* in, double2* out, int rank,
   const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)ctx->sm_count * 16);
   permute_kernel<<<blocks, 256, 0, ctx->stream>>>(in, out, L, total);
   ctx->launches++;
+  ctx->engine_count[6]++;
   TNCB_CUDA(cudaGetLastError());
   return TNCB_OK;
 }

@@ -156,11 +156,42 @@ static void collect_leaf_nodes(const tncb_tn* tn, std::vector<const tncb_tn*>& v
   for (size_t i = 0; i < tn->n_children; i++) collect_leaf_nodes(&tn->children[i], v);
 }
 
+// A schedule may be executed on a network other than the one it was compiled from (tncb_plan_execute):
+// every leaf must still have the kind, rank, dims and a payload that the plan's offsets were sized for.
+static int validate_leaves(const Schedule& S, const std::vector<const tncb_tn*>& leaves) {
+  if (leaves.size() != S.n_leaves_total) return fail(TNCB_ERR_INVALID, "network does not match the plan (leaf count)");
+  std::vector<const SlotMeta*> meta(leaves.size(), nullptr);
+  for (const SlotMeta& m : S.slots) if (m.leaf_index >= 0) meta[m.leaf_index] = &m;
+  for (size_t li = 0; li < leaves.size(); li++) {
+    const tncb_tn* lf = leaves[li];
+    if (S.leaf_kind[li] != lf->kind) return fail(TNCB_ERR_INVALID, "network payload kinds do not match the plan (leaf " + std::to_string(li) + ")");
+    if (lf->kind == TNCB_DATA_UNCONTRACTED) continue;
+    const SlotMeta* m = meta[li];
+    if (!m) return fail(TNCB_ERR_INVALID, "plan has no slot for leaf " + std::to_string(li));
+    if (lf->rank != (int)m->dims.size() || (lf->rank > 0 && !lf->dims))
+      return fail(TNCB_ERR_SHAPE, "leaf " + std::to_string(li) + ": rank differs from the plan");
+    for (int i = 0; i < lf->rank; i++)
+      if (lf->dims[i] != m->dims[i]) return fail(TNCB_ERR_SHAPE, "leaf " + std::to_string(li) + ": bond dimensions differ from the plan");
+    if (lf->kind == TNCB_DATA_MATRIX && !lf->host_re_im) return fail(TNCB_ERR_INVALID, "matrix leaf " + std::to_string(li) + " without host data");
+    if (lf->kind == TNCB_DATA_GATE && !lf->gate_name) return fail(TNCB_ERR_GATE, "gate leaf " + std::to_string(li) + " without a name");
+    if (lf->kind == TNCB_DATA_DEVICE) {
+      if (!lf->device || !lf->device->ptr) return fail(TNCB_ERR_UNCONTRACTED, "device leaf " + std::to_string(li) + " without a tensor handle (already consumed?)");
+      if (lf->device->elems != m->elems) return fail(TNCB_ERR_SHAPE, "device leaf " + std::to_string(li) + ": element count mismatch");
+    }
+  }
+  for (size_t x = 0; x < leaves.size(); x++)       // the same device handle twice would be freed twice
+    if (leaves[x]->kind == TNCB_DATA_DEVICE)
+      for (size_t y = x + 1; y < leaves.size(); y++)
+        if (leaves[y]->kind == TNCB_DATA_DEVICE && leaves[y]->device == leaves[x]->device)
+          return fail(TNCB_ERR_INVALID, "the same device tensor is passed as two leaves");
+  return TNCB_OK;
+}
+
 static int execute(tncb_ctx* ctx, const Schedule& S, const tncb_tn* tn, tncb_tensor** out, int* n_out, uint64_t* out_legs) {
   TNCB_CUDA(cudaSetDevice(ctx->device));
   std::vector<const tncb_tn*> leaves;
   collect_leaf_nodes(tn, leaves);
-  if (leaves.size() != S.n_leaves_total) return fail(TNCB_ERR_INVALID, "network does not match the plan");
+  { int vrc = validate_leaves(S, leaves); if (vrc) return vrc; }
   // ---- stage all host payloads, one H2D copy ----
   const size_t block_bytes = S.leaf_block_elems * sizeof(double2);
   void* leaf_block = nullptr;
@@ -200,6 +231,7 @@ static int execute(tncb_ctx* ctx, const Schedule& S, const tncb_tn* tn, tncb_ten
     else live[s].ptr = (double2*)leaf_block + S.leaf_offset[li];
   }
   int rc = TNCB_OK;
+  std::vector<tncb_tensor*> consumed;
   // TNCB_TRACE=1: per-step device times on stderr (tuning aid; adds two events per pair)
   const bool trace = std::getenv("TNCB_TRACE") != nullptr;
   std::vector<cudaEvent_t> tev;
@@ -213,9 +245,11 @@ static int execute(tncb_ctx* ctx, const Schedule& S, const tncb_tn* tn, tncb_ten
     live[st.out].ptr = (double2*)p; live[st.out].bytes = bytes;
     if ((rc = launch_pair(ctx, st.plan, live[st.a].ptr, live[st.b].ptr, live[st.out].ptr))) break;
     for (int s : {st.a, st.b}) { // operands are consumed (mem::take, contraction.rs:61-62)
-      if (live[s].handle) { tncb_tensor_free(ctx, live[s].handle); live[s].handle = nullptr; }
+      // caller-owned device leaves are released only after the WHOLE schedule was enqueued (atomic consumption:
+      // on any error every device input is still alive and owned by the caller, see tncb.h)
+      if (live[s].handle) consumed.push_back(live[s].handle);
       else if (live[s].bytes) ctx->arena.free(live[s].ptr, live[s].bytes);
-      live[s].ptr = nullptr; live[s].bytes = 0;
+      live[s].ptr = nullptr; live[s].bytes = 0; live[s].handle = nullptr;
     }
     if (trace) cudaEventRecord(tev[++step_no], ctx->stream);
   }
@@ -239,8 +273,8 @@ static int execute(tncb_ctx* ctx, const Schedule& S, const tncb_tn* tn, tncb_ten
     for (size_t i = 0; i < rm.dims.size(); i++) result->dims[i] = rm.dims[i];
     if (rl.bytes) { // produced by a pair: hand the arena block over
       result->ptr = rl.ptr; result->bytes = rl.bytes; rl.bytes = 0;
-    } else if (rl.handle) { // a device leaf that was never contracted
-      *result = *rl.handle; delete rl.handle; rl.handle = nullptr;
+    } else if (rl.handle) { // a device leaf that was never contracted: the result takes its storage over
+      *result = *rl.handle; rl.handle->ptr = nullptr; rl.handle->bytes = 0; consumed.push_back(rl.handle); rl.handle = nullptr;
     } else { // an uploaded leaf that was never contracted: copy it out of the leaf block
       result->bytes = std::max<size_t>(rm.elems * sizeof(double2), 16);
       void* p = nullptr;
@@ -255,7 +289,8 @@ static int execute(tncb_ctx* ctx, const Schedule& S, const tncb_tn* tn, tncb_ten
   for (size_t s = 0; s < live.size(); s++)
     if (live[s].bytes) ctx->arena.free(live[s].ptr, live[s].bytes);
   if (leaf_block) ctx->arena.free(leaf_block, block_bytes);
-  if (rc) return rc;
+  if (rc) return rc;                                 // nothing in `consumed` was touched
+  for (tncb_tensor* h : consumed) tncb_tensor_free(ctx, h);
   if (out) *out = result; else if (result) tncb_tensor_free(ctx, result);
   if (n_out) *n_out = S.result_slot >= 0 ? (int)S.slots[S.result_slot].legs.size() : 0;
   if (out_legs && S.result_slot >= 0)
@@ -353,13 +388,14 @@ static int execute_graph(tncb_ctx* ctx, tncb_plan* P, const tncb_tn* tn, tncb_te
   TNCB_CUDA(cudaSetDevice(ctx->device));
   std::vector<const tncb_tn*> leaves;
   collect_leaf_nodes(tn, leaves);
-  if (leaves.size() != S.n_leaves_total) return fail(TNCB_ERR_INVALID, "network does not match the plan");
-  const size_t block_bytes = std::max<size_t>(S.leaf_block_elems * sizeof(double2), 16);
   int rc;
+  if ((rc = validate_leaves(S, leaves))) return rc;
+  const size_t block_bytes = std::max<size_t>(S.leaf_block_elems * sizeof(double2), 16);
   if (!P->exec) {
-    P->ctx = ctx;
-    if ((rc = ctx->arena.alloc(P->ws_bytes, &P->ws))) return rc;
-    TNCB_CUDA(cudaMallocHost(&P->stage, block_bytes));
+    // (re-entered after a failed first call: keep what is already allocated instead of leaking it)
+    if (!P->ctx) { P->ctx = ctx; ctx->plans.push_back(P); }
+    if (!P->ws && (rc = ctx->arena.alloc(P->ws_bytes, &P->ws))) return rc;
+    if (!P->stage) TNCB_CUDA(cudaMallocHost(&P->stage, block_bytes));
   } else {
     TNCB_CUDA(cudaStreamSynchronize(ctx->stream));   // the previous replay may still read the staging buffer
   }
@@ -379,11 +415,14 @@ static int execute_graph(tncb_ctx* ctx, tncb_plan* P, const tncb_tn* tn, tncb_te
     ctx->partial_override = nullptr; ctx->partial_override_elems = 0;
     cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
     P->kernels_per_run = ctx->launches - launches_before;
-    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-    if (ce != cudaSuccess) return fail(TNCB_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
+    if (rc) { if (graph) cudaGraphDestroy(graph); ctx->launches = launches_before; return rc; }
+    if (ce != cudaSuccess) { ctx->launches = launches_before; P->graphable = false; return fail(TNCB_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce)); }
     ce = cudaGraphInstantiate(&P->exec, graph, 0);
     cudaGraphDestroy(graph);
-    if (ce != cudaSuccess) { P->exec = nullptr; return fail(TNCB_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(ce)); }
+    if (ce != cudaSuccess) {   // the plan falls back to the eager executor from now on
+      P->exec = nullptr; P->graphable = false; ctx->launches = launches_before;
+      return fail(TNCB_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(ce));
+    }
     ctx->launches = launches_before;
   }
   TNCB_CUDA(cudaGraphLaunch(P->exec, ctx->stream));
@@ -455,15 +494,24 @@ int tncb_plan_info(const tncb_plan* plan, uint64_t* n_pairs, double* flops, doub
   return TNCB_OK;
 }
 
+// Releases everything a plan holds on its context (graph, workspace, staging) and detaches it.  Called by
+// tncb_plan_destroy and by tncb_ctx_destroy for plans that outlive their context (either order is safe).
+void tncb_plan_release_device_state(tncb_plan* plan) {
+  tncb_ctx* ctx = plan->ctx;
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (plan->exec) { cudaGraphExecDestroy(plan->exec); plan->exec = nullptr; }
+  if (plan->ws) { ctx->arena.free(plan->ws, plan->ws_bytes); plan->ws = nullptr; }
+  if (plan->stage) { cudaFreeHost(plan->stage); plan->stage = nullptr; }
+  for (size_t i = 0; i < ctx->plans.size(); i++)
+    if (ctx->plans[i] == plan) { ctx->plans.erase(ctx->plans.begin() + i); break; }
+  plan->ctx = nullptr;
+}
+
 void tncb_plan_destroy(tncb_plan* plan) {
   if (!plan) return;
-  if (plan->ctx) {
-    cudaSetDevice(plan->ctx->device);
-    cudaStreamSynchronize(plan->ctx->stream);
-    if (plan->exec) cudaGraphExecDestroy(plan->exec);
-    if (plan->ws) plan->ctx->arena.free(plan->ws, plan->ws_bytes);
-    if (plan->stage) cudaFreeHost(plan->stage);
-  }
+  tncb_plan_release_device_state(plan);
   delete plan;
 }
 

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cmath>
 
 namespace tncb {
 
@@ -116,6 +117,10 @@ int tncb_ctx_create(int device, size_t arena_bytes, tncb_ctx** out) {
   ctx->sm_count = prop.multiProcessorCount;
   ctx->arena.capacity_limit = arena_bytes;
   if (const char* e = std::getenv("TNCB_OZAKI_SLICES")) ctx->oz_slices = std::max(0, std::min(8, atoi(e)));
+  if (const char* e = std::getenv("TNCB_TCGEN05_ENGINE")) ctx->oz_engine = atoi(e) == 1 ? 1 : 0;
+  if (const char* e = std::getenv("TNCB_CRT_MODULI")) ctx->crt_nmod_force = std::max(0, std::min(20, atoi(e)));
+  if (const char* e = std::getenv("TNCB_CRT_GROUP")) ctx->crt_group = std::max(1, atoi(e));
+  if (const char* e = std::getenv("TNCB_CRT_WS_GB")) ctx->crt_ws_bytes = (size_t)std::max(1, atoi(e)) << 30;
   cudaError_t se = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (se != cudaSuccess) { delete ctx; return fail(TNCB_ERR_CUDA, cudaGetErrorString(se)); }
   // keep freed workspace memory in the stream-ordered pool
@@ -132,6 +137,7 @@ void tncb_ctx_destroy(tncb_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  while (!ctx->plans.empty()) tncb_plan_release_device_state(ctx->plans.back());   // plans may outlive the ctx
   tncb_comm_destroy(ctx);
   if (ctx->tab) cudaFree(ctx->tab);
   if (ctx->partial) cudaFree(ctx->partial);
@@ -161,6 +167,7 @@ int tncb_ctx_stats(tncb_ctx* ctx, uint64_t* kernel_launches, uint64_t* arena_pea
 int tncb_ctx_reset_stats(tncb_ctx* ctx) {
   if (!ctx) return fail(TNCB_ERR_INVALID, "ctx is null");
   ctx->launches = 0; ctx->arena.peak = ctx->arena.live;
+  for (int i = 0; i < 8; i++) ctx->engine_count[i] = 0;
   return TNCB_OK;
 }
 
@@ -171,9 +178,66 @@ int tncb_ctx_set_tcgen05_slices(tncb_ctx* ctx, int slices) {
   return TNCB_OK;
 }
 
+int tncb_ctx_set_tcgen05_engine(tncb_ctx* ctx, int engine) {
+  if (!ctx || (engine != 0 && engine != 1)) return fail(TNCB_ERR_INVALID, "engine must be 0 (modular / CRT) or 1 (digit slicing)");
+  ctx->oz_engine = engine;
+  return TNCB_OK;
+}
+
+int tncb_ctx_set_tolerance(tncb_ctx* ctx, double rel) {
+  if (!ctx || !(rel >= 0.0) || rel >= 1.0) return fail(TNCB_ERR_INVALID, "tolerance must be in [0, 1)");
+  ctx->crt_tol = rel;
+  return TNCB_OK;
+}
+
+int tncb_ctx_set_tcgen05_moduli(tncb_ctx* ctx, int n_moduli) {
+  if (!ctx || (n_moduli != 0 && (n_moduli < 2 || n_moduli > 20))) return fail(TNCB_ERR_INVALID, "n_moduli must be 0 (auto) or in [2, 20]");
+  ctx->crt_nmod_force = n_moduli;
+  return TNCB_OK;
+}
+
+int tncb_tcgen05_bound(uint64_t k, double rel, int n_moduli_force, int* n_moduli, int* bits_a, int* bits_b, double* bound) {
+  if (k == 0 || (n_moduli_force != 0 && (n_moduli_force < 2 || n_moduli_force > 20))) return fail(TNCB_ERR_INVALID, "bad argument");
+  int n, a, b;
+  crt_choose((long long)k, crt_bits_for_tolerance((long long)k, rel), n_moduli_force, &n, &a, &b);
+  if (n_moduli) *n_moduli = n;
+  if (bits_a) *bits_a = a;
+  if (bits_b) *bits_b = b;
+  // truncation of a: < 2^(eA-a) per part, of b: < 2^(eB-b); 2K real products each way per real output; 2^e <= 2 max
+  if (bound) *bound = 4.0 * (double)k * (std::ldexp(1.0, 1 - a) + std::ldexp(1.0, 1 - b));
+  return TNCB_OK;
+}
+
+int tncb_ctx_set_tcgen05_workspace(tncb_ctx* ctx, size_t bytes) {
+  if (!ctx || bytes < ((size_t)1 << 20)) return fail(TNCB_ERR_INVALID, "workspace must be >= 1 MiB");
+  ctx->crt_ws_bytes = bytes;
+  return TNCB_OK;
+}
+
+int tncb_tcgen05_tables(int n_moduli, int* moduli, double* rho1, double* rho2, double* log2_product) {
+  if (n_moduli < 2 || n_moduli > 20) return fail(TNCB_ERR_INVALID, "n_moduli must be in [2, 20]");
+  return crt_export_tables(n_moduli, moduli, rho1, rho2, log2_product);
+}
+
+int tncb_ctx_engine_counts(tncb_ctx* ctx, uint64_t counts[8]) {
+  if (!ctx || !counts) return fail(TNCB_ERR_INVALID, "null argument");
+  for (int i = 0; i < 8; i++) counts[i] = ctx->engine_count[i];
+  return TNCB_OK;
+}
+
+int tncb_ctx_last_tcgen05_info(tncb_ctx* ctx, double* int8_ops, int* n_moduli) {
+  if (!ctx) return fail(TNCB_ERR_INVALID, "ctx is null");
+  if (int8_ops) *int8_ops = ctx->last_int8_ops;
+  if (n_moduli) *n_moduli = ctx->last_nmod;
+  return TNCB_OK;
+}
+
 int tncb_ctx_set_tcgen05_threshold(tncb_ctx* ctx, long long min_tiles, long long min_k) {
   if (!ctx || min_tiles < 1 || min_k < 1) return fail(TNCB_ERR_INVALID, "bad argument");
   ctx->oz_min_tiles = min_tiles; ctx->oz_min_k = min_k;
+  // the modular engine: the same call routes every pair with M, N >= 128 and K >= min_k to it when min_tiles == 1
+  ctx->crt_min_k = min_k;
+  ctx->crt_min_mnk = min_tiles <= 1 ? 0.0 : 268435456.0;
   return TNCB_OK;
 }
 

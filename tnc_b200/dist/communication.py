@@ -4,7 +4,7 @@
   reference (MPI, host memory)                      here
   ------------------------------------------------  ---------------------------------------------
   broadcast_path / broadcast_serializing :32-69     torch.distributed object broadcast (metadata)
-  get_tensor_mapping :89-115                        tncb_fanin_mapping (C ABI; ascending order)
+  get_tensor_mapping :89-115                        tncb_fanin_mapping (C ABI; FxHashMap walk order)
   scatter_tensor_network :125-195                   metadata scatter; leaves are uploaded by the
                                                     owning rank straight to its GPU
   send_tensor / receive_tensor :72-85 (postcard,    tncb_comm_send / tncb_comm_recv: raw complex128
@@ -49,8 +49,8 @@ def broadcast_path(path, root: int = 0, group=None):
 
 def get_tensor_mapping(path: ContractionPath, size: int) -> Dict[int, int]:
     """partition index -> rank (communication.rs:89-115).  The partition on the left of the
-    last top-level pair goes to rank 0, the others to 1, 2, ... in ascending partition index
-    (the reference iterates an FxHashMap; its own KAT shows 0->0, 2->1, 1->2 for that order)."""
+    last top-level pair goes to rank 0, the others to 1, 2, ... in the reference's FxHashMap walk
+    order (reproduced inside tncb_fanin_mapping; KAT communication.rs:257-279: 0->0, 2->1, 1->2)."""
     parts = sorted(path.nested)
     if not parts and not path.toplevel:
         return {0: 0}

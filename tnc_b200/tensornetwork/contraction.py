@@ -11,7 +11,7 @@ from typing import List, Optional
 import numpy as np
 
 from .. import Context, DeviceTensor, default_context
-from .._lib import TncbPath, TncbTn, check, u64_array
+from .._lib import TncbError, TncbPath, TncbTn, check, u64_array
 from ..contractionpath import ContractionPath
 from .tensor import Tensor
 from .tensordata import TensorData
@@ -54,6 +54,8 @@ class _Marshal:
         elif td.kind == "matrix":
             m = td.matrix
             if isinstance(m, DeviceTensor):
+                if m.handle is None:   # consumed by an earlier call (the Rust move left TensorData::Uncontracted behind)
+                    raise TncbError(-3, "Cannot convert uncontracted tensor to data (device tensor already consumed)")
                 node.kind = 3
                 node.device = m.handle
                 self.device_inputs.append(m)
