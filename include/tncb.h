@@ -112,6 +112,9 @@ int tncb_ctx_last_tcgen05_info(tncb_ctx* ctx, double* int8_ops, int* n_moduli);
  * with CUDA events on the ctx stream; tncb_ctx_last_gemm_ms synchronises and returns the last one. */
 int tncb_ctx_time_gemm(tncb_ctx* ctx, int enable);
 int tncb_ctx_last_gemm_ms(tncb_ctx* ctx, float* ms);
+/* enable = 2: every launch of the tcgen05 GEMM kernel is bracketed; tncb_ctx_gemm_totals synchronises, returns the
+ * summed device time, the executed int8 operations (2 x MAC, padded tiles) and the launch count, and resets. */
+int tncb_ctx_gemm_totals(tncb_ctx* ctx, double* ms, double* int8_ops, uint64_t* launches);
 
 /* ---- tensors: replaces tetra::Tensor::{new_from_flat, elements, shape, ndim}
  *      (tnc/src/tensornetwork/tensordata.rs:31-37, tnc/src/io/hdf5.rs:105-106) ---- */
@@ -228,6 +231,11 @@ int tncb_plan_create(tncb_ctx* ctx, const tncb_tn* tn, const tncb_path* path, tn
  * destroyed before or after its context. */
 int tncb_plan_execute(tncb_ctx* ctx, tncb_plan* plan, const tncb_tn* tn,
                       tncb_tensor** out, int* n_out, uint64_t* out_legs);
+/* Keep the materialised leaves of `tn` on the device (one H2D), then execute the schedule any number of times with no
+ * host work besides the kernel launches: the "inputs already resident in HBM" mode.  Not for plans with
+ * TNCB_DATA_DEVICE leaves (consumed per call) -> TNCB_ERR_UNSUPPORTED. */
+int tncb_plan_stage(tncb_ctx* ctx, tncb_plan* plan, const tncb_tn* tn);
+int tncb_plan_run(tncb_ctx* ctx, tncb_plan* plan, tncb_tensor** out, int* n_out, uint64_t* out_legs);
 /* Schedule facts: #pairs, sum 8MNK, sum 16(MK+KN+MN), peak arena bytes, #kernels. */
 int tncb_plan_info(const tncb_plan* plan, uint64_t* n_pairs, double* flops, double* bytes,
                    uint64_t* peak_bytes, uint64_t* n_kernels);

@@ -196,3 +196,36 @@ def test_sliced_equals_flat(ctx):
     got = contract_sliced(tn, p, legs, ctx=ctx)
     assert got.legs == ref.legs
     assert np.abs(got.to_numpy() - ref.to_numpy()).max() <= 1e-12
+
+
+@pytest.mark.parametrize("name,qubits,rounds", [("C3", 24, 12), ("C4", 36, 10)])
+def test_baseline_networks_vs_oracle(built_lib, name, qubits, rounds):
+    """BASELINE.json configs 3 and 4 as networks (seed 1, greedy Cotengrust path): the amplitude through
+    contract_tensor_network against the oracle port of the same network and path (CPU: ~5 s / ~8 s), rel 1e-9
+    (SURVEY 8d).  These are the only networks whose dominant pairs hit K1' (tcgen05) and K1 split-K in anger, so the
+    engine counters are part of the assertion (VERDICT r1 weak #2)."""
+    import torch
+    import tnc_b200 as tb
+    from tnc_b200.builders import random_circuit
+    from tnc_b200.tensornetwork import contract_tensor_network
+    tn = random_circuit(qubits, rounds, 0.5, 0.5, np.random.default_rng(1))
+    path = greedy(tn)
+    c = tb.Context(0)
+    try:
+        c.reset_stats()
+        res = contract_tensor_network(tn, path, ctx=c)
+        got = complex(res.to_numpy())
+        ec = c.engine_counts()
+        c.set_tcgen05_slices(0)                       # the same network on the FP64 pipe only
+        got_dmma = complex(contract_tensor_network(tn, path, ctx=c).to_numpy())
+    finally:
+        c.close()
+    torch.set_num_threads(max(1, min(16, torch.get_num_threads())))
+    ref = complex(orc.contract_tensor_network(to_oracle(tn), to_opath(path), backend="torch").data)
+    assert res.legs == []
+    assert abs(got - ref) <= 1e-9 * abs(ref), (name, got, ref)
+    assert abs(got_dmma - ref) <= 1e-9 * abs(ref), (name, got_dmma, ref)
+    assert ec["k1_tcgen05"] >= 1 and ec["k1_dmma"] + ec["k1_dmma_splitk"] >= 1 and ec["k0"] >= 100, ec
+    if name == "C4":
+        assert ec["k1_dmma_splitk"] >= 1, ec      # the M=256, N=64, K=2^20 pair
+    print(f"{name}: |gpu-cpu|/|cpu| = {abs(got - ref) / abs(ref):.2e} (tcgen05 on), {abs(got_dmma - ref) / abs(ref):.2e} (DMMA only); engines {ec}")

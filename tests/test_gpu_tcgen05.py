@@ -33,7 +33,7 @@ def dmma_ctx(built_lib):
     c.close()
 
 
-def check(ctx, rng, a_legs, a_dims, b_legs, b_dims, tol=1e-12, scale_rows=False):
+def check(ctx, rng, a_legs, a_dims, b_legs, b_dims, tol=1e-12, scale_rows=False, engine="k1_tcgen05"):
     import tnc_b200 as tb
     a, b = rand_c(rng, a_dims), rand_c(rng, b_dims)
     if scale_rows:  # wildly different magnitudes per slice of the leading free legs -> per-row exponents matter
@@ -41,7 +41,7 @@ def check(ctx, rng, a_legs, a_dims, b_legs, b_dims, tol=1e-12, scale_rows=False)
         b = b * np.exp(rng.uniform(-40, 40, size=[b_dims[0]] + [1] * (len(b_dims) - 1)))
     ctx.reset_stats()
     legs, got = tb.contract_pair(ctx, a_legs, a, b_legs, b)
-    assert ctx.engine_counts()["k1_tcgen05"] == 1, ctx.engine_counts()
+    assert ctx.engine_counts()[engine] == 1, ctx.engine_counts()
     ref_legs, ref = orc.contract_pair(a_legs, a, b_legs, b)
     assert legs == ref_legs and got.shape == ref.shape
     err = np.abs(got - ref).max()
@@ -61,7 +61,7 @@ def test_engine_is_really_tcgen05(tc_ctx):
     tc_ctx.reset_stats()
     tb.contract_pair_into(tc_ctx, [0, 1], a, [1, 2], b, c)
     assert tc_ctx.stats()["kernel_launches"] == 6
-    assert tc_ctx.engine_counts()["k1_tcgen05"] == 1 and tc_ctx.last_tcgen05_info()["n_moduli"] == 16
+    assert tc_ctx.engine_counts()["k1_tcgen05"] == 1 and tc_ctx.last_tcgen05_info()["n_moduli"] == tb.tcgen05_bound(256)["n_moduli"] == 15
     tc_ctx.set_tcgen05_engine(1)                               # legacy digit slicing: 2 exponent + 2 slicing + 1 GEMM
     tc_ctx.reset_stats()
     tb.contract_pair_into(tc_ctx, [0, 1], a, [1, 2], b, c)
@@ -86,7 +86,8 @@ def test_tcgen05_square(tc_ctx):
 def test_tcgen05_ragged(tc_ctx):
     rng = np.random.default_rng(2)
     check(tc_ctx, rng, [0, 1], [300, 333], [1, 2], [333, 260])      # M, N, K not multiples of 128
-    check(tc_ctx, rng, [0, 1, 2], [7, 41, 300], [2, 3, 1], [300, 257, 41])  # permuted K legs, K = 287*... ragged
+    check(tc_ctx, rng, [0, 1, 2], [7, 41, 300], [2, 3, 1], [300, 257, 41], engine="k0_splitk")  # M = 7: too thin for tcgen05 -> K0 split-K
+    check(tc_ctx, rng, [0, 1, 2], [133, 41, 30], [2, 3, 1], [30, 257, 41])   # permuted K legs (K = 1230), ragged everywhere
     check(tc_ctx, rng, [0, 1], [130, 129], [1, 2], [129, 131])
 
 

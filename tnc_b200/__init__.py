@@ -73,8 +73,14 @@ class Context:
     def set_tcgen05_threshold(self, min_tiles: int, min_k: int) -> None:
         check(self._l.tncb_ctx_set_tcgen05_threshold(self.handle, int(min_tiles), int(min_k)))
 
-    def time_gemm(self, enable: bool = True) -> None:
+    def time_gemm(self, enable=True) -> None:
+        """False/0 off, True/1 last launch of the dominant GEMM kernel, 2 accumulate every tcgen05 GEMM launch."""
         check(self._l.tncb_ctx_time_gemm(self.handle, int(enable)))
+
+    def gemm_totals(self) -> dict:
+        ms, ops, n = C.c_double(), C.c_double(), C.c_uint64()
+        check(self._l.tncb_ctx_gemm_totals(self.handle, C.byref(ms), C.byref(ops), C.byref(n)))
+        return {"ms": ms.value, "int8_ops": ops.value, "launches": n.value}
 
     def last_gemm_ms(self) -> float:
         ms = C.c_float()

@@ -69,6 +69,7 @@ SIGNATURES = {
     "tncb_ctx_last_tcgen05_info": (C.c_int, [C.c_void_p, f64p, i32p]),
     "tncb_ctx_set_tcgen05_threshold": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong]),
     "tncb_ctx_time_gemm": (C.c_int, [C.c_void_p, C.c_int]),
+    "tncb_ctx_gemm_totals": (C.c_int, [C.c_void_p, f64p, f64p, u64p]),
     "tncb_ctx_last_gemm_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "tncb_tensor_upload": (C.c_int, [C.c_void_p, C.c_int, u64p, C.c_void_p, vpp]),
     "tncb_tensor_alloc": (C.c_int, [C.c_void_p, C.c_int, u64p, vpp]),
@@ -92,6 +93,8 @@ SIGNATURES = {
     "tncb_contract_tensor_network": (C.c_int, [C.c_void_p, C.POINTER(TncbTn), C.POINTER(TncbPath), vpp, i32p, u64p]),
     "tncb_plan_create": (C.c_int, [C.c_void_p, C.POINTER(TncbTn), C.POINTER(TncbPath), vpp]),
     "tncb_plan_execute": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(TncbTn), vpp, i32p, u64p]),
+    "tncb_plan_stage": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(TncbTn)]),
+    "tncb_plan_run": (C.c_int, [C.c_void_p, C.c_void_p, vpp, i32p, u64p]),
     "tncb_plan_info": (C.c_int, [C.c_void_p, u64p, f64p, f64p, u64p, u64p]),
     "tncb_plan_destroy": (None, [C.c_void_p]),
     "tncb_comm_unique_id": (C.c_int, [C.c_void_p]),

@@ -146,39 +146,51 @@ __device__ __forceinline__ int crt_exp_from_bits(unsigned long long bits) {
 template <bool ROWFAST>
 __global__ void __launch_bounds__(256)
 crt_rowmax_kernel(const double2* __restrict__ src, const long long* __restrict__ off_row, const long long* __restrict__ off_k,
-                  long long rows, long long K, int k_tiles_per_cta, unsigned long long* __restrict__ rowmax) {
+                  long long rows, long long K, unsigned long long* __restrict__ rowmax) {
   __shared__ unsigned long long s_max[RES_ROWS_C];
-  const long long row0 = (long long)blockIdx.x * RES_ROWS_C;
+  const long long row0 = (long long)blockIdx.x * RES_ROWS_C, k0 = (long long)blockIdx.y * RES_K_C;
   const int tid = threadIdx.x;
   if (tid < RES_ROWS_C) s_max[tid] = 0ull;
   __syncthreads();
-  const int r = ROWFAST ? (tid % RES_ROWS_C) : (tid / 8);            // ROWFAST: lanes walk rows; else 8 threads per row
-  unsigned long long m = 0ull;
-  if (row0 + r < rows) {
-    const long long base = __ldg(off_row + row0 + r);
-    const long long kbeg = (long long)blockIdx.y * k_tiles_per_cta * RES_K_C;
-    const long long kend = min(K, kbeg + (long long)k_tiles_per_cta * RES_K_C);
-    const int kstep = ROWFAST ? 256 / RES_ROWS_C : 8;
-    for (long long k = kbeg + (ROWFAST ? tid / RES_ROWS_C : (tid & 7)); k < kend; k += kstep) {
-      const double2 v = __ldg(src + base + __ldg(off_k + k));
-      const unsigned long long bx = (unsigned long long)__double_as_longlong(fabs(v.x));
-      const unsigned long long by = (unsigned long long)__double_as_longlong(fabs(v.y));
-      m = max(m, max(bx, by));
+  // one 32 x 128 tile per CTA, 16 independent loads per thread (same element -> thread map as the residue kernel)
+  unsigned long long m[RES_ROWS_C * RES_K_C / 256];
+#pragma unroll
+  for (int it = 0; it < RES_ROWS_C * RES_K_C / 256; it++) {
+    const int e = it * 256 + tid;
+    const int r = ROWFAST ? (e % RES_ROWS_C) : (e / RES_K_C);
+    const int k = ROWFAST ? (e / RES_ROWS_C) : (e % RES_K_C);
+    m[it] = 0ull;
+    if (row0 + r < rows && k0 + k < K) {
+      const double2 v = __ldg(src + __ldg(off_row + row0 + r) + __ldg(off_k + k0 + k));
+      m[it] = max((unsigned long long)__double_as_longlong(fabs(v.x)), (unsigned long long)__double_as_longlong(fabs(v.y)));
     }
-    atomicMax(&s_max[r], m);
+  }
+  if (ROWFAST) {   // a thread's 16 elements belong to ONE row (e % 32 is constant over it)
+    unsigned long long mm = 0ull;
+#pragma unroll
+    for (int it = 0; it < RES_ROWS_C * RES_K_C / 256; it++) mm = max(mm, m[it]);
+    if (mm) atomicMax(&s_max[tid % RES_ROWS_C], mm);
+  } else {         // iteration `it` covers rows 2 it and 2 it + 1: reduce over the 128 threads of each row first
+#pragma unroll
+    for (int it = 0; it < RES_ROWS_C * RES_K_C / 256; it++) {
+      unsigned long long mm = m[it];
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) mm = max(mm, __shfl_xor_sync(0xffffffffu, mm, d));
+      if ((tid & 31) == 0 && mm) atomicMax(&s_max[2 * it + (tid >> 7)], mm);
+    }
   }
   __syncthreads();
   if (tid < RES_ROWS_C && row0 + tid < rows && s_max[tid] != 0ull) atomicMax(rowmax + row0 + tid, s_max[tid]);
 }
 
 // Tile of 32 rows x 128 k: load (coalesced along whichever index is contiguous in the source), scale +
-// truncate to integer-valued doubles in shared memory, then every thread reduces 16 consecutive k of one row
-// modulo every m_i and writes 16 bytes per plane.
+// truncate to integer-valued doubles in shared memory, then every thread reduces 2 x 8 consecutive k of one row
+// modulo every m_i and writes 8 bytes per plane and pass.
 // planes: [((mod * COMPS + comp) * rowsP + row) * Kp + k];  COMPS == 2: (re, im) -- Bt side,
 // COMPS == 3: (-im, re, im) -- At side.
-constexpr int RES_ROWS = RES_ROWS_C, RES_K = RES_K_C, RES_RS = RES_K + RES_K / 16 + 1;   // padded row stride (elements)
+constexpr int RES_ROWS = RES_ROWS_C, RES_K = RES_K_C, RES_RS = RES_K + RES_K / 8 + 1;   // padded row stride (elements)
 template <int COMPS, bool ROWFAST>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 crt_residue_kernel(const double2* __restrict__ src, const long long* __restrict__ off_row, const long long* __restrict__ off_k,
                    long long rows, long long K, long long rowsP, long long Kp, const unsigned long long* __restrict__ rowmax, int bits,
                    const __grid_constant__ CrtTables T, int8_t* __restrict__ planes) {
@@ -207,45 +219,53 @@ crt_residue_kernel(const double2* __restrict__ src, const long long* __restrict_
       v.y = trunc(v.y * sc * two_a);
       if (sc == 0.0) { v.x = 0.0; v.y = 0.0; }   // (Inf * 0 = NaN)
     }
-    tile[r * RES_RS + k + (k >> 4)] = v;
+    tile[r * RES_RS + k + (k >> 3)] = v;
   }
   __syncthreads();
-  const int r = tid >> 3, kg = tid & 7;
+  const int r = tid >> 3;
   if (row0 + r >= rows) return;
-  double xr[16], xi[16];
-#pragma unroll
-  for (int j = 0; j < 16; j++) { const double2 v = tile[r * RES_RS + kg * 17 + j]; xr[j] = v.x; xi[j] = v.y; }
-  const double RMAGIC = 6755399441055744.0;   // 1.5 * 2^52: (x + RMAGIC) - RMAGIC = rint(x); low word of (x + RMAGIC) = int(x)
+  const double RMAGIC = 6755399441055744.0;   // 1.5 * 2^52: the low word of (x + RMAGIC) is rint(x) mod 2^32
   const long long plane_stride = rowsP * Kp;
-  int8_t* dst = planes + (row0 + r) * Kp + k0 + kg * 16;
-  for (int i = 0; i < T.nmod; i++) {
-    const double m = (double)T.mod[i], inv = T.inv_mod[i];
-    uint32_t wr[4] = {0, 0, 0, 0}, wi[4] = {0, 0, 0, 0};
+#pragma unroll 1
+  for (int pass = 0; pass < 2; pass++) {
+    const int g = (tid & 7) + 8 * pass;        // group of 8 consecutive k
+    double xr[8], xi[8];
+    int lr[8], li[8];                           // the integers x mod 2^32
 #pragma unroll
-    for (int j = 0; j < 16; j++) {
-      // q = rint(x / m) (one rounding: the product is exact inside the FMA); r = x - q m exactly.
-      // |x inv - x/m| <= 2^53/m * 2^-53 < 0.006, so |r| <= 0.506 m: <= 127 for every odd m <= 253, and for
-      // m = 256 the byte wrap (128 -> -128) is itself a valid representative.
-      const double qr = fma(xr[j], inv, RMAGIC) - RMAGIC;
-      const double qi = fma(xi[j], inv, RMAGIC) - RMAGIC;
-      const int rr = __double2loint(fma(-qr, m, xr[j]) + RMAGIC);
-      const int ri = __double2loint(fma(-qi, m, xi[j]) + RMAGIC);
-      constexpr uint32_t sel[4] = {0x3214u, 0x3240u, 0x3410u, 0x4210u};   // low byte of the 2nd operand into byte j & 3
-      wr[j >> 2] = __byte_perm(wr[j >> 2], (uint32_t)rr, sel[j & 3]);
-      wi[j >> 2] = __byte_perm(wi[j >> 2], (uint32_t)ri, sel[j & 3]);
+    for (int j = 0; j < 8; j++) {
+      const double2 v = tile[r * RES_RS + g * 9 + j];
+      xr[j] = v.x; xi[j] = v.y;
+      lr[j] = (int)__double2ll_rn(v.x); li[j] = (int)__double2ll_rn(v.y);
     }
-    const uint4 r4 = make_uint4(wr[0], wr[1], wr[2], wr[3]);
-    const uint4 i4 = make_uint4(wi[0], wi[1], wi[2], wi[3]);
-    int8_t* d = dst + (long long)i * COMPS * plane_stride;
-    if (COMPS == 2) {
-      *reinterpret_cast<uint4*>(d) = r4;
-      *reinterpret_cast<uint4*>(d + plane_stride) = i4;
-    } else {
-      // byte-wise negation: |ri| <= 127 for odd m; for m = 256 the wrap -(-128) = -128 is again == 128 (mod 256)
-      const uint4 n4 = make_uint4(__vneg4(wi[0]), __vneg4(wi[1]), __vneg4(wi[2]), __vneg4(wi[3]));
-      *reinterpret_cast<uint4*>(d) = n4;
-      *reinterpret_cast<uint4*>(d + plane_stride) = r4;
-      *reinterpret_cast<uint4*>(d + 2 * plane_stride) = i4;
+    int8_t* dst = planes + (row0 + r) * Kp + k0 + g * 8;
+#pragma unroll 1
+    for (int i = 0; i < T.nmod; i++) {
+      const int m = T.mod[i];
+      const double inv = T.inv_mod[i];
+      uint32_t wr[2] = {0, 0}, wi[2] = {0, 0};
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        // q = rint(x / m): ONE rounding (the product is exact inside the FMA, the sum has ulp 1); its low 32 bits are
+        // the low word of the sum.  r = x - q m is tiny, so computing it modulo 2^32 in int32 is exact.
+        // |x inv - x/m| <= 2^53/m * 2^-53 < 0.006  =>  |r| <= 0.506 m: <= 127 for every odd m <= 253, and for
+        // m = 256 the byte wrap (128 -> -128) is itself a valid representative.
+        const int qr = __double2loint(fma(xr[j], inv, RMAGIC));
+        const int qi = __double2loint(fma(xi[j], inv, RMAGIC));
+        const int rr = lr[j] - qr * m, ri = li[j] - qi * m;
+        constexpr uint32_t sel[4] = {0x3214u, 0x3240u, 0x3410u, 0x4210u};   // low byte of the 2nd operand into byte j & 3
+        wr[j >> 2] = __byte_perm(wr[j >> 2], (uint32_t)rr, sel[j & 3]);
+        wi[j >> 2] = __byte_perm(wi[j >> 2], (uint32_t)ri, sel[j & 3]);
+      }
+      int8_t* d = dst + (long long)i * COMPS * plane_stride;
+      if (COMPS == 2) {
+        *reinterpret_cast<uint2*>(d) = make_uint2(wr[0], wr[1]);
+        *reinterpret_cast<uint2*>(d + plane_stride) = make_uint2(wi[0], wi[1]);
+      } else {
+        // byte-wise negation: |ri| <= 127 for odd m; for m = 256 the wrap -(-128) = -128 is again == 128 (mod 256)
+        *reinterpret_cast<uint2*>(d) = make_uint2(__vneg4(wi[0]), __vneg4(wi[1]));
+        *reinterpret_cast<uint2*>(d + plane_stride) = make_uint2(wr[0], wr[1]);
+        *reinterpret_cast<uint2*>(d + 2 * plane_stride) = make_uint2(wi[0], wi[1]);
+      }
     }
   }
 }
@@ -309,7 +329,7 @@ __device__ __forceinline__ void c_tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 
 struct CrtGemmArgs {
-  int8_t* R;          // residues [((mod * nkc + kc) * 2 + comp) * Np + n] * Mp + m
+  int8_t* R;          // residues + 128 as bytes: [((mod * nkc + kc) * 2 + comp) * Np + n] * Mp + m
   int Np, Mp;         // padded plane rows of this panel (Np % 256 == 0, Mp % 128 == 0)
   int pairs_n, tiles_m;
   int nmod, nkc, kb_per_chunk, num_kb;
@@ -419,7 +439,7 @@ crt_gemm_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant_
       c_commit_2sm(&tfull_bar[buf]);
     }
   } else if (warp >= 2) {
-    // ================= epilogue (both CTAs; own 128 rows): acc mod m_i -> int8 =================
+    // ================= epilogue (both CTAs; own 128 rows): acc mod m_i -> one (offset) byte =================
     const int q = warp & 3;     // TMEM lane quarter this warp may read
     int f = 0;
     for (int item = cluster_id; item < p.total_items; item += n_clusters, f++) {
@@ -443,8 +463,8 @@ crt_gemm_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant_
           const int a = (int)v[j];
           // q = round(a / m) within 1/4 (|a| < 2^31, |magic / 2^32 - 1/m| <= 2^-33): |z| <= 0.75 m <= 192
           const int qq = (int)(((long long)a * magic + 0x80000000LL) >> 32);
-          int z = a - qq * m;
-          z -= ((z + 128) >> 8) * m;                   // one wrap into [-128, 127]
+          int z = a - qq * m + 128;
+          z -= (z >> 8) * m;                           // one wrap: the residue as an OFFSET byte z + 128 in [0, 255]
           constexpr uint32_t sel[4] = {0x3214u, 0x3240u, 0x3410u, 0x4210u};
           if ((j & 3) == 0) wds[j >> 2] = 0;
           wds[j >> 2] = __byte_perm(wds[j >> 2], (uint32_t)z, sel[j & 3]);
@@ -475,44 +495,63 @@ struct CrtReconArgs {
   int nkc;
 };
 
-// one thread: 4 consecutive m of one row n
+// one thread: 8 consecutive m of one row n.  No conversion-pipe instruction in the inner loop: a residue byte u = y + 128
+// becomes the double 2^52 + u by a byte permute into the low mantissa word, one DADD removes 2^52 + 128 nkc.
+template <bool ONE_CHUNK>
 __global__ void __launch_bounds__(256)
 crt_reconstruct_kernel(const __grid_constant__ CrtReconArgs a, const __grid_constant__ CrtTables T) {
-  const long long cols4 = a.Mp >> 2;
+  const long long cols8 = a.Mp >> 3;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long n = idx / cols4, m4 = (idx - n * cols4) * 4;
-  if (n >= a.rows || m4 >= a.cols) return;
-  double s1r[4] = {0, 0, 0, 0}, s2r[4] = {0, 0, 0, 0}, s1i[4] = {0, 0, 0, 0}, s2i[4] = {0, 0, 0, 0};
+  const long long n = idx / cols8, m8 = (idx - n * cols8) * 8;
+  if (n >= a.rows || m8 >= a.cols) return;
+  double s1r[8], s2r[8], s1i[8], s2i[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) { s1r[j] = s2r[j] = s1i[j] = s2i[j] = 0.0; }
   const long long plane = a.Np * a.Mp;
-  const int8_t* base = a.R + n * a.Mp + m4;
+  const int8_t* base = a.R + n * a.Mp + m8;
+  const double bias = 4503599627370496.0 + 128.0 * (double)a.nkc;   // 2^52 + 128 per chunk
+#pragma unroll 4
   for (int i = 0; i < T.nmod; i++) {
-    int yr[4] = {0, 0, 0, 0}, yi[4] = {0, 0, 0, 0};
-    for (int c = 0; c < a.nkc; c++) {           // residues of the K chunks add up (still == C' mod m_i)
-      const int8_t* pr = base + (long long)((i * a.nkc + c) * 2) * plane;
-      const uint32_t wr = __ldg(reinterpret_cast<const uint32_t*>(pr));
-      const uint32_t wi = __ldg(reinterpret_cast<const uint32_t*>(pr + plane));
+    uint32_t ur[8], ui[8];     // byte sums over the K chunks (still == C' + 128 nkc mod m_i)
+    if (ONE_CHUNK) {
+      const uint2 wr = __ldg(reinterpret_cast<const uint2*>(base + (long long)(i * 2) * plane));
+      const uint2 wi = __ldg(reinterpret_cast<const uint2*>(base + (long long)(i * 2 + 1) * plane));
 #pragma unroll
       for (int j = 0; j < 4; j++) {
-        yr[j] += (int)(int8_t)(wr >> (8 * j));
-        yi[j] += (int)(int8_t)(wi >> (8 * j));
+        ur[j] = __byte_perm(wr.x, 0, 0x4440 + j); ur[4 + j] = __byte_perm(wr.y, 0, 0x4440 + j);
+        ui[j] = __byte_perm(wi.x, 0, 0x4440 + j); ui[4 + j] = __byte_perm(wi.y, 0, 0x4440 + j);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; j++) { ur[j] = 0; ui[j] = 0; }
+      for (int c = 0; c < a.nkc; c++) {
+        const int8_t* pr = base + (long long)((i * a.nkc + c) * 2) * plane;
+        const uint2 wr = __ldg(reinterpret_cast<const uint2*>(pr));
+        const uint2 wi = __ldg(reinterpret_cast<const uint2*>(pr + plane));
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          ur[j] += __byte_perm(wr.x, 0, 0x4440 + j); ur[4 + j] += __byte_perm(wr.y, 0, 0x4440 + j);
+          ui[j] += __byte_perm(wi.x, 0, 0x4440 + j); ui[4 + j] += __byte_perm(wi.y, 0, 0x4440 + j);
+        }
       }
     }
     const double r1 = T.rho1[i], r2 = T.rho2[i];
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
+    for (int j = 0; j < 8; j++) {
       // y * rho1 is exact (|y| <= 2^12, rho1 on a 2^-34 grid) and so is the sum over <= 20 moduli (|S1| < 2^17)
-      const double dr = (double)yr[j], di = (double)yi[j];
+      const double dr = __hiloint2double(0x43300000, (int)ur[j]) - bias;
+      const double di = __hiloint2double(0x43300000, (int)ui[j]) - bias;
       s1r[j] = fma(dr, r1, s1r[j]); s2r[j] = fma(dr, r2, s2r[j]);
       s1i[j] = fma(di, r1, s1i[j]); s2i[j] = fma(di, r2, s2i[j]);
     }
   }
   const int en = crt_exp_from_bits(a.max_n[n]);
-  double2* dst = a.C + n * a.ldc + m4;
+  double2* dst = a.C + n * a.ldc + m8;
   const double RMAGIC = 6755399441055744.0;
 #pragma unroll
-  for (int j = 0; j < 4; j++) {
-    if (m4 + j >= a.cols) break;
-    const int em = crt_exp_from_bits(a.max_m[m4 + j]);
+  for (int j = 0; j < 8; j++) {
+    if (m8 + j >= a.cols) break;
+    const int em = crt_exp_from_bits(a.max_m[m8 + j]);
     double2 out;
     if (en == kExpNonFinite || em == kExpNonFinite) {
       out = make_double2(__longlong_as_double(0x7ff8000000000000LL), __longlong_as_double(0x7ff8000000000000LL));
@@ -624,9 +663,6 @@ int launch_k1_crt(tncb_ctx* ctx, const PairPlan& P, const double2* A, const doub
   const bool b_rowfast = !P.b_kfast, a_rowfast = !P.a_kfast;
   ctx->last_int8_ops = 0.0; ctx->last_nmod = nmod;
   bool timed = false;
-  // row-maximum pass: each CTA covers 32 rows x kt_per_cta k-tiles (one atomic per row and CTA)
-  const int k_tiles = (int)(Kp / RES_K);
-  const int kt_per_cta = std::max(1, std::min(k_tiles, 8));
 
   for (long long n0 = 0; n0 < P.N; n0 += pn) {
     const long long nrows = std::min(pn, P.N - n0);
@@ -635,10 +671,9 @@ int launch_k1_crt(tncb_ctx* ctx, const PairPlan& P, const double2* A, const doub
     if (Np != nrows) cudaMemsetAsync(pb, 0, (size_t)nmod * 2 * Np * Kp, st);
     cudaMemsetAsync(max_n, 0, (size_t)nrows * sizeof(unsigned long long), st);
     {
-      dim3 gm((unsigned)((nrows + RES_ROWS - 1) / RES_ROWS), (unsigned)((k_tiles + kt_per_cta - 1) / kt_per_cta));
-      if (b_rowfast) crt_rowmax_kernel<true><<<gm, 256, 0, st>>>(B, offBn + n0, offBk, nrows, P.K, kt_per_cta, max_n);
-      else crt_rowmax_kernel<false><<<gm, 256, 0, st>>>(B, offBn + n0, offBk, nrows, P.K, kt_per_cta, max_n);
       dim3 g((unsigned)((nrows + RES_ROWS - 1) / RES_ROWS), (unsigned)(Kp / RES_K));
+      if (b_rowfast) crt_rowmax_kernel<true><<<g, 256, 0, st>>>(B, offBn + n0, offBk, nrows, P.K, max_n);
+      else crt_rowmax_kernel<false><<<g, 256, 0, st>>>(B, offBn + n0, offBk, nrows, P.K, max_n);
       if (b_rowfast) crt_residue_kernel<2, true><<<g, 256, smem_res, st>>>(B, offBn + n0, offBk, nrows, P.K, Np, Kp, max_n, bits_b, T, (int8_t*)pb);
       else crt_residue_kernel<2, false><<<g, 256, smem_res, st>>>(B, offBn + n0, offBk, nrows, P.K, Np, Kp, max_n, bits_b, T, (int8_t*)pb);
     }
@@ -651,10 +686,9 @@ int launch_k1_crt(tncb_ctx* ctx, const PairPlan& P, const double2* A, const doub
       if (Mp != mcols) cudaMemsetAsync(pa, 0, (size_t)nmod * 3 * Mp * Kp, st);
       cudaMemsetAsync(max_m, 0, (size_t)mcols * sizeof(unsigned long long), st);
       {
-        dim3 gm((unsigned)((mcols + RES_ROWS - 1) / RES_ROWS), (unsigned)((k_tiles + kt_per_cta - 1) / kt_per_cta));
-        if (a_rowfast) crt_rowmax_kernel<true><<<gm, 256, 0, st>>>(A, offAm + m0, offAk, mcols, P.K, kt_per_cta, max_m);
-        else crt_rowmax_kernel<false><<<gm, 256, 0, st>>>(A, offAm + m0, offAk, mcols, P.K, kt_per_cta, max_m);
         dim3 g((unsigned)((mcols + RES_ROWS - 1) / RES_ROWS), (unsigned)(Kp / RES_K));
+        if (a_rowfast) crt_rowmax_kernel<true><<<g, 256, 0, st>>>(A, offAm + m0, offAk, mcols, P.K, max_m);
+        else crt_rowmax_kernel<false><<<g, 256, 0, st>>>(A, offAm + m0, offAk, mcols, P.K, max_m);
         if (a_rowfast) crt_residue_kernel<3, true><<<g, 256, smem_res, st>>>(A, offAm + m0, offAk, mcols, P.K, Mp, Kp, max_m, bits_a, T, (int8_t*)pa);
         else crt_residue_kernel<3, false><<<g, 256, smem_res, st>>>(A, offAm + m0, offAk, mcols, P.K, Mp, Kp, max_m, bits_a, T, (int8_t*)pa);
       }
@@ -678,16 +712,19 @@ int launch_k1_crt(tncb_ctx* ctx, const PairPlan& P, const double2* A, const doub
       attr[0].id = cudaLaunchAttributeClusterDimension;
       attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr; cfg.numAttrs = 1;
-      if (ctx->time_gemm && !timed) cudaEventRecord(ctx->gemm_ev0, st);
+      const double ops = 2.0 * 4.0 * (double)nmod * (double)Np * (double)Mp * (double)Kp;
+      const bool time_this = ctx->time_gemm == 2 || (ctx->time_gemm == 1 && !timed);
+      if (time_this) gemm_timer_begin(ctx);
       cudaError_t e = cudaLaunchKernelEx(&cfg, crt_gemm_kernel, mapB, mapA, g);
-      if (ctx->time_gemm && !timed) { cudaEventRecord(ctx->gemm_ev1, st); ctx->gemm_ev_valid = true; timed = true; }
+      if (time_this) { gemm_timer_end(ctx, ops); timed = true; }
       if (e != cudaSuccess) { cleanup(); return fail(TNCB_ERR_CUDA, std::string("crt_gemm_kernel launch: ") + cudaGetErrorString(e)); }
-      ctx->last_int8_ops += 2.0 * 4.0 * (double)nmod * (double)Np * (double)Mp * (double)Kp;
+      ctx->last_int8_ops += ops;
       CrtReconArgs r;
       r.R = (const int8_t*)pr; r.C = C + n0 * P.M + m0; r.max_n = max_n; r.max_m = max_m;
       r.rows = nrows; r.cols = mcols; r.ldc = P.M; r.Np = Np; r.Mp = Mp; r.nkc = nkc;
-      const long long threads = nrows * (Mp / 4);
-      crt_reconstruct_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(r, T);
+      const long long threads = nrows * (Mp / 8);
+      if (nkc == 1) crt_reconstruct_kernel<true><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(r, T);
+      else crt_reconstruct_kernel<false><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(r, T);
       ctx->launches += 2;
     }
   }

@@ -85,7 +85,9 @@ struct tncb_ctx {
   size_t crt_ws_bytes = (size_t)12 << 30; int crt_group = 8;
   double last_int8_ops = 0.0; int last_nmod = 0;
   uint64_t engine_count[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // K0, K0 split-K, K1 DMMA, K1 DMMA split-K, K1' tcgen05, K2, permute, -
-  bool time_gemm = false; cudaEvent_t gemm_ev0 = nullptr, gemm_ev1 = nullptr; bool gemm_ev_valid = false;
+  // dominant-kernel timing: 0 off, 1 keep the last launch (gemm_ev0/1), 2 accumulate every launch (event pool)
+  int time_gemm = 0; cudaEvent_t gemm_ev0 = nullptr, gemm_ev1 = nullptr; bool gemm_ev_valid = false;
+  std::vector<cudaEvent_t> gemm_pool; size_t gemm_used = 0; std::vector<double> gemm_ops;
   int sm_count = 148;
   // pinned staging for leaf uploads
   void* stage_host = nullptr; size_t stage_bytes = 0;
@@ -123,6 +125,9 @@ int launch_k1_crt(tncb_ctx* ctx, const PairPlan& p, const double2* A, const doub
 void crt_choose(long long K, int want_bits, int nmod_force, int* nmod, int* bits_a, int* bits_b);
 int crt_bits_for_tolerance(long long K, double tol);
 int crt_export_tables(int nmod, int* moduli, double* rho1, double* rho2, double* log2_product);
+
+void gemm_timer_begin(tncb_ctx* ctx);              // brackets one launch of the dominant GEMM kernel (K1 / K1')
+void gemm_timer_end(tncb_ctx* ctx, double ops);    // ops: executed int8 ops (K1') or flops (K1) of that launch
 
 int ensure_partial(tncb_ctx* ctx, size_t elems);
 size_t k0_partial_elems(int sm_count, const PairPlan& p);

@@ -474,9 +474,9 @@ static int launch_k1_cfg(tncb_ctx* ctx, const K1Args& a) {
   TNCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long tiles = (long long)a.tiles_m * a.tiles_n * a.ksplit;
   if (tiles > 0x7fffffffLL) return fail(TNCB_ERR_UNSUPPORTED, "K1 grid too large");
-  if (ctx->time_gemm) cudaEventRecord(ctx->gemm_ev0, ctx->stream);
+  if (ctx->time_gemm == 1) gemm_timer_begin(ctx);       // (accumulate mode collects the tcgen05 GEMMs only)
   kern<<<(unsigned)tiles, WN * WM * 32, smem, ctx->stream>>>(a);
-  if (ctx->time_gemm) { cudaEventRecord(ctx->gemm_ev1, ctx->stream); ctx->gemm_ev_valid = true; }
+  if (ctx->time_gemm == 1) gemm_timer_end(ctx, 8.0 * (double)a.M * (double)a.N * (double)a.K);
   ctx->launches++;
   TNCB_CUDA(cudaGetLastError());
   return TNCB_OK;

@@ -187,13 +187,15 @@ static int validate_leaves(const Schedule& S, const std::vector<const tncb_tn*>&
   return TNCB_OK;
 }
 
-static int execute(tncb_ctx* ctx, const Schedule& S, const tncb_tn* tn, tncb_tensor** out, int* n_out, uint64_t* out_legs) {
+// `resident` != nullptr: the leaf block already sits on the device (tncb_plan_stage); `tn` may then be null.
+static int execute(tncb_ctx* ctx, const Schedule& S, const tncb_tn* tn, tncb_tensor** out, int* n_out, uint64_t* out_legs,
+                   const double2* resident = nullptr) {
   TNCB_CUDA(cudaSetDevice(ctx->device));
   std::vector<const tncb_tn*> leaves;
-  collect_leaf_nodes(tn, leaves);
-  { int vrc = validate_leaves(S, leaves); if (vrc) return vrc; }
+  if (tn) collect_leaf_nodes(tn, leaves);
+  if (!resident) { int vrc = validate_leaves(S, leaves); if (vrc) return vrc; }
   // ---- stage all host payloads, one H2D copy ----
-  const size_t block_bytes = S.leaf_block_elems * sizeof(double2);
+  const size_t block_bytes = resident ? 0 : S.leaf_block_elems * sizeof(double2);
   void* leaf_block = nullptr;
   if (block_bytes) {
     if (ctx->stage_bytes < block_bytes) {
@@ -228,7 +230,7 @@ static int execute(tncb_ctx* ctx, const Schedule& S, const tncb_tn* tn, tncb_ten
     const int li = S.slots[s].leaf_index;
     if (li < 0) continue;
     if (S.leaf_kind[li] == TNCB_DATA_DEVICE) { live[s].ptr = leaves[li]->device->ptr; live[s].handle = leaves[li]->device; }
-    else live[s].ptr = (double2*)leaf_block + S.leaf_offset[li];
+    else live[s].ptr = (resident ? const_cast<double2*>(resident) : (double2*)leaf_block) + S.leaf_offset[li];
   }
   int rc = TNCB_OK;
   std::vector<tncb_tensor*> consumed;
@@ -313,6 +315,8 @@ struct tncb_plan {
   void* stage = nullptr;             // plan-owned pinned staging of the leaf block
   cudaGraphExec_t exec = nullptr;
   uint64_t kernels_per_run = 0;
+  void* resident = nullptr;          // device copy of the leaf block (tncb_plan_stage), arena block of `resident_bytes`
+  size_t resident_bytes = 0;
 };
 
 namespace tncb {
@@ -470,6 +474,38 @@ int tncb_plan_execute(tncb_ctx* ctx, tncb_plan* plan, const tncb_tn* tn, tncb_te
   return tncb::execute(ctx, plan->S, tn, out, n_out, out_legs);
 }
 
+// Materialise the leaves of `tn` once and keep them on the device; tncb_plan_run then executes the schedule without
+// any host work besides the kernel launches (the "inputs already resident in HBM" measurement, and the shared leaf
+// block of sliced execution).
+int tncb_plan_stage(tncb_ctx* ctx, tncb_plan* plan, const tncb_tn* tn) {
+  if (!ctx || !plan || !tn) return tncb::fail(TNCB_ERR_INVALID, "null argument");
+  const tncb::Schedule& S = plan->S;
+  for (int k : S.leaf_kind) if (k == TNCB_DATA_DEVICE) return tncb::fail(TNCB_ERR_UNSUPPORTED, "plans with device leaves cannot be staged (they are consumed per call)");
+  if (plan->ctx && plan->ctx != ctx) return tncb::fail(TNCB_ERR_INVALID, "plan belongs to another context");
+  TNCB_CUDA(cudaSetDevice(ctx->device));
+  std::vector<const tncb_tn*> leaves;
+  tncb::collect_leaf_nodes(tn, leaves);
+  int rc = tncb::validate_leaves(S, leaves);
+  if (rc) return rc;
+  const size_t bytes = std::max<size_t>(S.leaf_block_elems * sizeof(double2), 16);
+  std::vector<std::complex<double>> host(std::max<size_t>(S.leaf_block_elems, 1));
+  if ((rc = tncb::stage_leaves(S, leaves, host.data()))) return rc;
+  if (!plan->ctx) { plan->ctx = ctx; ctx->plans.push_back(plan); }
+  if (!plan->resident) {
+    if ((rc = ctx->arena.alloc(bytes, &plan->resident))) return rc;
+    plan->resident_bytes = bytes;
+  }
+  TNCB_CUDA(cudaMemcpyAsync(plan->resident, host.data(), S.leaf_block_elems * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
+  TNCB_CUDA(cudaStreamSynchronize(ctx->stream));   // `host` dies with this frame
+  return TNCB_OK;
+}
+
+int tncb_plan_run(tncb_ctx* ctx, tncb_plan* plan, tncb_tensor** out, int* n_out, uint64_t* out_legs) {
+  if (!ctx || !plan) return tncb::fail(TNCB_ERR_INVALID, "null argument");
+  if (!plan->resident || plan->ctx != ctx) return tncb::fail(TNCB_ERR_INVALID, "tncb_plan_stage has not been called on this context");
+  return tncb::execute(ctx, plan->S, nullptr, out, n_out, out_legs, (const double2*)plan->resident);
+}
+
 int tncb_plan_info(const tncb_plan* plan, uint64_t* n_pairs, double* flops, double* bytes, uint64_t* peak_bytes, uint64_t* n_kernels) {
   if (!plan) return tncb::fail(TNCB_ERR_INVALID, "plan is null");
   const tncb::Schedule& S = plan->S;
@@ -504,6 +540,7 @@ void tncb_plan_release_device_state(tncb_plan* plan) {
   if (plan->exec) { cudaGraphExecDestroy(plan->exec); plan->exec = nullptr; }
   if (plan->ws) { ctx->arena.free(plan->ws, plan->ws_bytes); plan->ws = nullptr; }
   if (plan->stage) { cudaFreeHost(plan->stage); plan->stage = nullptr; }
+  if (plan->resident) { ctx->arena.free(plan->resident, plan->resident_bytes); plan->resident = nullptr; }
   for (size_t i = 0; i < ctx->plans.size(); i++)
     if (ctx->plans[i] == plan) { ctx->plans.erase(ctx->plans.begin() + i); break; }
   plan->ctx = nullptr;

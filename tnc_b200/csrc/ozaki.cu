@@ -607,7 +607,8 @@ int launch_k1_ozaki(tncb_ctx* ctx, const PairPlan& P, const double2* A, const do
     const int smem2 = OZ2_STAGES * OZ2_STAGE_BYTES + 1024;
     cudaError_t e2 = cudaFuncSetAttribute(oz_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
     if (e2 != cudaSuccess) { cleanup(); return fail(TNCB_ERR_CUDA, cudaGetErrorString(e2)); }
-    if (ctx->time_gemm) cudaEventRecord(ctx->gemm_ev0, st);
+    const double ops2 = 2.0 * 4.0 * (S * (S + 1) / 2) * (double)Np * (double)Mp * (double)Kp;
+    if (ctx->time_gemm) gemm_timer_begin(ctx);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(Np / OZ_BT), (unsigned)(Mp / OZ_BT));   // n tiles on x
     cfg.blockDim = dim3(OZ_THREADS); cfg.dynamicSmemBytes = smem2; cfg.stream = st;
@@ -616,7 +617,8 @@ int launch_k1_ozaki(tncb_ctx* ctx, const PairPlan& P, const double2* A, const do
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     e2 = cudaLaunchKernelEx(&cfg, oz_gemm2_kernel, mapB, mapA, a);
-    if (ctx->time_gemm) { cudaEventRecord(ctx->gemm_ev1, st); ctx->gemm_ev_valid = true; }
+    if (ctx->time_gemm) gemm_timer_end(ctx, ops2);
+    ctx->last_int8_ops = ops2; ctx->last_nmod = 0;
     ctx->launches++;
     cleanup();
     if (e2 != cudaSuccess) return fail(TNCB_ERR_CUDA, std::string("2-CTA launch: ") + cudaGetErrorString(e2));
@@ -625,7 +627,7 @@ int launch_k1_ozaki(tncb_ctx* ctx, const PairPlan& P, const double2* A, const do
   auto kern = cl ? oz_gemm_kernel<true> : oz_gemm_kernel<false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   if (e != cudaSuccess) { cleanup(); return fail(TNCB_ERR_CUDA, cudaGetErrorString(e)); }
-  if (ctx->time_gemm) cudaEventRecord(ctx->gemm_ev0, st);
+  if (ctx->time_gemm) gemm_timer_begin(ctx);
   if (cl) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid; cfg.blockDim = dim3(OZ_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
@@ -638,7 +640,7 @@ int launch_k1_ozaki(tncb_ctx* ctx, const PairPlan& P, const double2* A, const do
   } else {
     kern<<<grid, OZ_THREADS, smem_bytes, st>>>(mapB, mapA, a);
   }
-  if (ctx->time_gemm) { cudaEventRecord(ctx->gemm_ev1, st); ctx->gemm_ev_valid = true; }
+  if (ctx->time_gemm) gemm_timer_end(ctx, 2.0 * 4.0 * (S * (S + 1) / 2) * (double)Np * (double)Mp * (double)Kp);
   ctx->launches++;
   e = cudaGetLastError();
   cleanup();  // stream-ordered reuse: later allocations are only touched by later kernels

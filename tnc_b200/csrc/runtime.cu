@@ -76,6 +76,25 @@ void Arena::release_all() {
   slabs.clear(); reserved = live = 0;
 }
 
+void gemm_timer_begin(tncb_ctx* ctx) {
+  if (ctx->time_gemm == 1) cudaEventRecord(ctx->gemm_ev0, ctx->stream);
+  else if (ctx->time_gemm == 2) {
+    if (ctx->gemm_used + 2 > ctx->gemm_pool.size()) {
+      cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+      ctx->gemm_pool.push_back(a); ctx->gemm_pool.push_back(b);
+    }
+    cudaEventRecord(ctx->gemm_pool[ctx->gemm_used], ctx->stream);
+  }
+}
+
+void gemm_timer_end(tncb_ctx* ctx, double ops) {
+  if (ctx->time_gemm == 1) { cudaEventRecord(ctx->gemm_ev1, ctx->stream); ctx->gemm_ev_valid = true; }
+  else if (ctx->time_gemm == 2) {
+    cudaEventRecord(ctx->gemm_pool[ctx->gemm_used + 1], ctx->stream);
+    ctx->gemm_used += 2; ctx->gemm_ops.push_back(ops);
+  }
+}
+
 int tensor_new(tncb_ctx* ctx, int rank, const uint64_t* dims, tncb_tensor** out) {
   if (rank < 0 || rank > kMaxLegs) return fail(TNCB_ERR_INVALID, "tensor rank out of range");
   tncb_tensor* t = new tncb_tensor();
@@ -143,6 +162,7 @@ void tncb_ctx_destroy(tncb_ctx* ctx) {
   if (ctx->partial) cudaFree(ctx->partial);
   if (ctx->stage_host) cudaFreeHost(ctx->stage_host);
   if (ctx->gemm_ev0) { cudaEventDestroy(ctx->gemm_ev0); cudaEventDestroy(ctx->gemm_ev1); }
+  for (cudaEvent_t e : ctx->gemm_pool) cudaEventDestroy(e);
   ctx->arena.release_all();
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -244,8 +264,26 @@ int tncb_ctx_set_tcgen05_threshold(tncb_ctx* ctx, long long min_tiles, long long
 int tncb_ctx_time_gemm(tncb_ctx* ctx, int enable) {
   if (!ctx) return fail(TNCB_ERR_INVALID, "ctx is null");
   TNCB_CUDA(cudaSetDevice(ctx->device));
+  if (enable < 0 || enable > 2) return fail(TNCB_ERR_INVALID, "enable must be 0, 1 (last launch) or 2 (accumulate)");
   if (enable && !ctx->gemm_ev0) { TNCB_CUDA(cudaEventCreate(&ctx->gemm_ev0)); TNCB_CUDA(cudaEventCreate(&ctx->gemm_ev1)); }
-  ctx->time_gemm = enable != 0; ctx->gemm_ev_valid = false;
+  ctx->time_gemm = enable; ctx->gemm_ev_valid = false; ctx->gemm_used = 0; ctx->gemm_ops.clear();
+  return TNCB_OK;
+}
+
+int tncb_ctx_gemm_totals(tncb_ctx* ctx, double* ms, double* ops, uint64_t* launches) {
+  if (!ctx) return fail(TNCB_ERR_INVALID, "ctx is null");
+  TNCB_CUDA(cudaSetDevice(ctx->device));
+  TNCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  double tms = 0.0, tops = 0.0;
+  for (size_t i = 0; i + 1 < ctx->gemm_used; i += 2) {
+    float t = 0.f;
+    TNCB_CUDA(cudaEventElapsedTime(&t, ctx->gemm_pool[i], ctx->gemm_pool[i + 1]));
+    tms += t; tops += ctx->gemm_ops[i / 2];
+  }
+  if (ms) *ms = tms;
+  if (ops) *ops = tops;
+  if (launches) *launches = ctx->gemm_used / 2;
+  ctx->gemm_used = 0; ctx->gemm_ops.clear();
   return TNCB_OK;
 }
 

@@ -130,6 +130,22 @@ class NetworkPlan:
         check(self.ctx._l.tncb_plan_info(self.handle, C.byref(n), C.byref(fl), C.byref(by), C.byref(pk), C.byref(k)))
         return {"pairs": n.value, "flops": fl.value, "bytes": by.value, "peak_bytes": pk.value, "kernels": k.value}
 
+    def stage(self, tn: Tensor) -> None:
+        """Materialise + upload the leaves once (tncb_plan_stage); `run()` then needs no host data."""
+        m = _Marshal()
+        c_tn = m.tn(tn)
+        check(self.ctx._l.tncb_plan_stage(self.ctx.handle, self.handle, C.byref(c_tn)))
+
+    def run(self) -> Tensor:
+        out, n_out, legs = C.c_void_p(), C.c_int(), u64_array([0] * 64)
+        check(self.ctx._l.tncb_plan_run(self.ctx.handle, self.handle, C.byref(out), C.byref(n_out), legs))
+        if not out.value:
+            return Tensor()
+        dt = DeviceTensor.adopt(self.ctx, out)
+        res = Tensor([legs[i] for i in range(n_out.value)], dt.shape)
+        res.set_tensor_data(TensorData.Matrix(dt))
+        return res
+
     def execute(self, tn: Tensor) -> Tensor:
         m = _Marshal()
         c_tn = m.tn(tn)

@@ -1,42 +1,66 @@
-"""DMMA (K1) vs tcgen05 int8 slicing (K1') over GEMM shapes: device time per pair, same box."""
-import sys, os, json
+"""DMMA (K1) vs the tcgen05 int8 engines (K1': modular/CRT with several modulus counts, legacy digit slicing) over GEMM
+shapes: device time per pair on the same box, error against the DMMA result.
+usage: python tools/sweep_engines.py [MxNxK ...]"""
+import json
+import os
+import sys
+
 import numpy as np
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+
 import tnc_b200 as tb
 
 ctx = tb.Context(0)
 stream = torch.cuda.ExternalStream(ctx.stream, device=0)
-shapes = [(512,512,512),(1024,1024,1024),(1536,1536,1536),(2048,2048,2048),(1024,1024,4096),(4096,4096,512),(4096,4096,256),
-          (2048,512,2048),(512,4096,4096),(8192,8192,1024),(16384,8192,4096)]
+shapes = [(256, 256, 256), (512, 512, 512), (1024, 1024, 1024), (2048, 2048, 2048), (4096, 4096, 4096), (1024, 1024, 4096), (4096, 4096, 512),
+          (4096, 4096, 256), (2048, 512, 2048), (512, 4096, 4096), (8192, 8192, 1024), (16384, 8192, 4096), (65536, 2048, 512), (256, 128, 262144)]
 if len(sys.argv) > 1:
     shapes = [tuple(int(x) for x in s.split("x")) for s in sys.argv[1:]]
 rng = np.random.default_rng(0)
+ctx.set_tcgen05_threshold(1, 128)
+
+
+def timed(reps=5):
+    for _ in range(2):
+        tb.contract_pair_into(ctx, [0, 1], a, [2, 0], b, c)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        tb.contract_pair_into(ctx, [0, 1], a, [2, 0], b, c)
+    e1.record(stream); ctx.synchronize(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
 for (M, N, K) in shapes:
     a = tb.DeviceTensor.from_numpy(ctx, (rng.standard_normal((K, M)) + 1j * rng.standard_normal((K, M))))
     b = tb.DeviceTensor.from_numpy(ctx, (rng.standard_normal((N, K)) + 1j * rng.standard_normal((N, K))))
     c = tb.DeviceTensor.empty(ctx, (N, M))
     out = {"M": M, "N": N, "K": K}
-    ref = None
-    for s in (0, 8, 7, 6):
-        ctx.set_tcgen05_slices(s)
-        os.environ["TNCB_FORCE_TCGEN05"] = "1"
-        for _ in range(2):
-            tb.contract_pair_into(ctx, [0, 1], a, [2, 0], b, c)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 5
-        e0.record(stream)
-        for _ in range(reps):
-            tb.contract_pair_into(ctx, [0, 1], a, [2, 0], b, c)
-        e1.record(stream); ctx.synchronize(); torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / reps
-        res = c.to_numpy() if M * N <= 2048 * 2048 else None
-        if s == 0:
-            ref = res
-            out["dmma_ms"] = round(ms, 4); out["dmma_tf"] = round(8.0 * M * N * K / ms * 1e-9, 1)
-        else:
-            out[f"s{s}_ms"] = round(ms, 4); out[f"s{s}_tf"] = round(8.0 * M * N * K / ms * 1e-9, 1)
-            if res is not None:
-                out[f"s{s}_err"] = float(np.abs(res - ref).max() / np.abs(ref).max())
+    small = M * N <= 2048 * 2048
+    ctx.set_tcgen05_slices(0)
+    ms = timed()
+    ref = c.to_numpy() if small else None
+    out["dmma_ms"] = round(ms, 4); out["dmma_tf"] = round(8.0 * M * N * K / ms * 1e-9, 1)
+    ctx.set_tcgen05_slices(8)
+    ctx.time_gemm(True)
+    for nm in (0, 14, 12):
+        ctx.set_tcgen05_moduli(nm)
+        ms = timed()
+        tag = f"crt{ctx.last_tcgen05_info()['n_moduli']}"
+        out[tag + "_ms"] = round(ms, 4); out[tag + "_tf"] = round(8.0 * M * N * K / ms * 1e-9, 1)
+        out[tag + "_gemm_ms"] = round(ctx.last_gemm_ms(), 4)
+        if small:
+            out[tag + "_err"] = float(np.abs(c.to_numpy() - ref).max() / np.abs(ref).max())
+    ctx.set_tcgen05_moduli(0)
+    if min(M, N, K) >= 256:
+        ctx.set_tcgen05_engine(1)
+        ms = timed()
+        out["slice8_ms"] = round(ms, 4); out["slice8_tf"] = round(8.0 * M * N * K / ms * 1e-9, 1)
+        if small:
+            out["slice8_err"] = float(np.abs(c.to_numpy() - ref).max() / np.abs(ref).max())
+        ctx.set_tcgen05_engine(0)
+    ctx.time_gemm(False)
     print(json.dumps(out), flush=True)
     a.free(); b.free(); c.free()
