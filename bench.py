@@ -50,6 +50,9 @@ WORKLOAD = ("36-qubit random-circuit amplitude network (10 rounds, p1=p2=0.5, Sy
 # DMMA m8n8k4 sustained, = 148 SM x 64 FMA/clk x 2 x 1.965 GHz.  tcgen05 has no f64 kind.
 FP64_TENSOR_PEAK_TFLOPS = 37.2
 INT8_NOMINAL_TOPS = 4500.0   # dense int8 tcgen05 (kind::i8), 2 x the nominal bf16 figure
+# Measured on this pool's B200 with tools/i8_peak.cu (profiles/r02_i8_peak.txt): back-to-back UMMA kind::i8 cta_group::2 from
+# resident shared memory, 4533 TOP/s sustained over 274 ms (4592 over 54 ms) -- the int8 tensor pipe at ~1.88 GHz.
+INT8_MEASURED_TOPS = 4533.0
 
 
 # ------------------------------------------------------------------------------------------------ inputs
@@ -78,7 +81,7 @@ def partition_plan(tn, n):
         path = ContractionPath({int(k): ContractionPath.simple([tuple(x) for x in v]) for k, v in p["nested"].items()},
                                [tuple(x) for x in p["toplevel"]])
         got = (partition_tensor_network(tn, p["partitioning"]), path,
-               {k: p[k] for k in ("critical_path_flops", "total_flops", "partition_sizes")})
+               {k: p[k] for k in ("critical_path_flops", "total_flops", "partition_sizes", "predicted_critical_path_ms", "chosen")})
     return got
 
 
@@ -483,9 +486,10 @@ def run_ours(args):
             traffic, tfile = _captured_traffic()
             line["roofline"] = {
                 "bound": "tensor", "kernel": "crt_gemm_kernel (tcgen05.mma.cta_group::2.kind::i8, TMA, TMEM; one int8 GEMM per modulus)",
-                "achieved": ach, "peak": 2.0 * bf16_meas, "unit": "int8 TOP/s", "frac": ach / (2.0 * bf16_meas),
-                "peak_source": "2 x measured bf16 burst (MEASURED_PEAKS.json) as the int8 proxy of measured; nominal dense int8 = 4500 TOP/s "
-                               f"(frac of nominal {ach / INT8_NOMINAL_TOPS:.3f})",
+                "achieved": ach, "peak": INT8_MEASURED_TOPS, "unit": "int8 TOP/s", "frac": ach / INT8_MEASURED_TOPS,
+                "peak_source": "int8 tensor-pipe peak measured on this pool with tools/i8_peak.cu (profiles/r02_i8_peak.txt, sustained); MEASURED_PEAKS.json "
+                               f"has no int8 entry: against its bf16 burst x 2 = {2.0 * bf16_meas:.0f} the fraction is {ach / (2.0 * bf16_meas):.3f}, against nominal 4500 "
+                               f"{ach / INT8_NOMINAL_TOPS:.3f}; ncu on the C2 launch: 96 % of the per-cycle pipe peak at a power-capped 1.50 GHz (profiles/r02_ncu_crt_gemm_summary.txt)",
                 "how": f"CUDA events around every one of the {gt['launches']} launches of the kernel inside the timed region (sum of durations "
                        f"{gt['ms']:.3f} ms = {gt['ms'] / total_ms:.2f} of it); executed int8 ops = 2 x 4 x moduli x Np x Mp x Kp (padded tiles)",
                 "kernel_ms_per_step": gt["ms"] / args.steps, "launches_per_step": gt["launches"] / args.steps,

@@ -96,9 +96,48 @@ def communication_path_cost(inputs: Sequence[Tensor], path, only_count_ops: bool
     return op, mem
 
 
+def _communication_custom_cost(inputs: Sequence[Tensor], path, cost_fn: Callable, only_critical_path: bool, tensor_cost: Sequence[float]):
+    """:259-289 with an arbitrary per-pair cost."""
+    cost = list(tensor_cost)
+    if len(inputs) == 1:
+        return cost[0], cost[0]
+    ts = list(inputs)
+    op, mem = 0.0, 0.0
+    for (i, j) in path:
+        mem = max(mem, contract_size_tensors(ts[i], ts[j]))
+        op = cost_fn(ts[i], ts[j]) + (max(cost[i], cost[j]) if only_critical_path else cost[i] + cost[j])
+        cost[i] = op
+        ts[i] = ts[i] ^ ts[j]
+    return op, mem
+
+
 def communication_path_op_costs(inputs: Sequence[Tensor], path, only_count_ops: bool,
                                 tensor_cost: Optional[Sequence[float]] = None):
     """:196-208: ((critical-path cost, serial cost), memory)."""
     par, _ = communication_path_cost(inputs, path, only_count_ops, True, tensor_cost)
     ser, mem = communication_path_cost(inputs, path, only_count_ops, False, tensor_cost)
     return (par, ser), mem
+
+
+# ---- planning-only device time model (NOT in the reference) -------------------------------------------------------
+# The reference scores partitionings by operation counts (contract_op_cost_tensors); on a B200 the pairs that dominate a
+# partitioned contraction are as often bandwidth-bound (boundary tensors of 2^28 elements) as compute-bound, and the
+# fan-in moves them over NVLink.  `gpu_time_tensors` is a two-roof estimate per pair, measured rates of this repo's
+# kernels (profiles/r02_engine_sweep.jsonl): K1' ~130 TFLOP/s-equivalent for GEMM-like pairs, ~30 TFLOP/s DMMA otherwise,
+# ~5 TB/s of HBM traffic, ~5 us per launch.  Used by tools/plan_partitions.py to choose among candidate partitionings.
+GPU_RATES = {"crt_flops": 130e12, "dmma_flops": 30e12, "hbm_bytes": 5e12, "launch_s": 5e-6, "nvlink_bytes": 6e11, "hop_s": 30e-6}
+
+
+def gpu_time_tensors(t1: Tensor, t2: Tensor) -> float:
+    k = (t1 & t2).size()
+    m, n = (t1 - t2).size(), (t2 - t1).size()
+    flops = 8.0 * m * n * k
+    crt = m >= 128 and n >= 128 and k >= 256 and m * n * k >= 2.0 ** 28
+    t_math = flops / (GPU_RATES["crt_flops"] if crt else GPU_RATES["dmma_flops"])
+    t_mem = 16.0 * (m * k + n * k + m * n) / GPU_RATES["hbm_bytes"]
+    return max(t_math, t_mem) + GPU_RATES["launch_s"]
+
+
+def gpu_fanin_time_tensors(t1: Tensor, t2: Tensor) -> float:
+    """a fan-in pair: t2 travels to t1's device first (ncclSend/Recv of the raw buffer), then the pair runs there"""
+    return gpu_time_tensors(t1, t2) + 16.0 * t2.size() / GPU_RATES["nvlink_bytes"] + GPU_RATES["hop_s"]

@@ -29,18 +29,21 @@ def communication_path_op_costs(inputs: Sequence[Tensor], path, tensor_cost: Seq
 LocalCache = Dict[Tuple, Tuple[List[Tuple[int, int]], float, Tuple[Tuple[int, ...], Tuple[int, ...]]]]
 
 
-def _local(tn: Tensor, ids: Tuple[int, ...], cache: Optional[LocalCache]):
+def _local(tn: Tensor, ids: Tuple[int, ...], cache: Optional[LocalCache], cost_fn=None):
     """greedy local path (replace-left) + op cost + external legs of one partition.  `cache` belongs to ONE
     call of compute_solution / balance_partitions (i.e. one network); its key also carries the members'
     legs and dims so that a cache can never answer for another network's tensors."""
-    key = (ids, tuple((tuple(tn.tensors[i].legs), tuple(tn.tensors[i].bond_dims)) for i in ids))
+    key = (ids, tuple((tuple(tn.tensors[i].legs), tuple(tn.tensors[i].bond_dims)) for i in ids), cost_fn)
     hit = cache.get(key) if cache is not None else None
     if hit is None:
         comp = Tensor.new_composite([tn.tensors[i] for i in ids])
         opt = Cotengrust(comp)
         opt.find_path()
         p = opt.get_best_replace_path()
-        cost, _ = contract_path_cost(comp.tensors, p, True)
+        if cost_fn is None:
+            cost, _ = contract_path_cost(comp.tensors, p, True)
+        else:
+            cost, _ = _cc._path_custom_cost(comp.tensors, p, cost_fn, _cc.contract_size_tensors)
         ext = comp.external_tensor()
         hit = (p.toplevel, cost, (tuple(ext.legs), tuple(ext.bond_dims)))
         if cache is not None:
@@ -48,9 +51,10 @@ def _local(tn: Tensor, ids: Tuple[int, ...], cache: Optional[LocalCache]):
     return hit
 
 
-def compute_solution(tn: Tensor, partitioning: Sequence[int], cache: Optional[LocalCache] = None):
+def compute_solution(tn: Tensor, partitioning: Sequence[int], cache: Optional[LocalCache] = None, cost_fn=None, fanin_cost_fn=None):
     """repartitioning.rs:25-76 with CommunicationScheme::Greedy: returns
-    (partitioned_tn, path, parallel_cost, sum_cost)."""
+    (partitioned_tn, path, parallel_cost, sum_cost).  `cost_fn` / `fanin_cost_fn` (default: the reference's operation
+    count) replace the per-pair cost of local and fan-in pairs, e.g. contraction_cost.gpu_time_tensors."""
     ptn = partition_tensor_network(tn, partitioning)
     ids_order: List[int] = []
     for p in partitioning:
@@ -59,14 +63,19 @@ def compute_solution(tn: Tensor, partitioning: Sequence[int], cache: Optional[Lo
     nested, costs, exts = {}, [], []
     for k, pid in enumerate(ids_order):
         ids = tuple(i for i, q in enumerate(partitioning) if q == pid)
-        top, cost, (el, ed) = _local(tn, ids, cache)
+        top, cost, (el, ed) = _local(tn, ids, cache, cost_fn)
         nested[k] = ContractionPath.simple(top)
         costs.append(cost)
         exts.append(Tensor(list(el), list(ed)))
     comm = Cotengrust(Tensor.new_composite(exts))
     comm.find_path()
     toplevel = comm.get_best_replace_path().toplevel
-    (par, ser), _ = communication_path_op_costs(exts, toplevel, costs)
+    if cost_fn is None and fanin_cost_fn is None:
+        (par, ser), _ = communication_path_op_costs(exts, toplevel, costs)
+    else:
+        f = fanin_cost_fn or cost_fn
+        par, _ = _cc._communication_custom_cost(exts, toplevel, f, True, costs)
+        ser, _ = _cc._communication_custom_cost(exts, toplevel, f, False, costs)
     return ptn, ContractionPath(nested, toplevel), par, ser
 
 
@@ -97,7 +106,8 @@ def _trial_move(tn: Tensor, num_partitions: int, cur: List[int], rng, cache: Opt
 
 
 def balance_partitions(tn: Tensor, num_partitions: int, initial: Sequence[int], steps: int = 400, seed: int = 42,
-                       n_trials: int = 8, restart_iter: int = 50, t_start: float = 2.0, t_end: float = 0.05) -> Tuple[List[int], float]:
+                       n_trials: int = 8, restart_iter: int = 50, t_start: float = 2.0, t_end: float = 0.05,
+                       cost_fn=None, fanin_cost_fn=None) -> Tuple[List[int], float]:
     """Simulated annealing over partitionings (score = critical-path op cost of `compute_solution`).
     Structure of simulated_annealing.rs:80-160: every iteration runs `n_trials` independent trial moves
     from the current solution (each accepted with probability exp(-log2(score/current)/T)), continues
@@ -108,7 +118,7 @@ def balance_partitions(tn: Tensor, num_partitions: int, initial: Sequence[int], 
     rng = np.random.default_rng(seed)
     cache: LocalCache = {}                     # per call: never shared between networks
     cur = list(initial)
-    _, _, cur_score, _ = compute_solution(tn, cur, cache)
+    _, _, cur_score, _ = compute_solution(tn, cur, cache, cost_fn, fanin_cost_fn)
     best, best_score = list(cur), cur_score
     iters = max(1, steps // n_trials)
     last_improvement = 0
@@ -119,7 +129,7 @@ def balance_partitions(tn: Tensor, num_partitions: int, initial: Sequence[int], 
             t_sol, t_score = cur, cur_score
             trial = _trial_move(tn, num_partitions, cur, rng, cache)
             if trial is not None:
-                _, _, score, _ = compute_solution(tn, trial, cache)
+                _, _, score, _ = compute_solution(tn, trial, cache, cost_fn, fanin_cost_fn)
                 if np.exp(-np.log2(score / cur_score) / temp) >= rng.random():
                     t_sol, t_score = trial, score
             if cand_score is None or t_score < cand_score:

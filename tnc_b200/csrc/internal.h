@@ -132,6 +132,19 @@ void gemm_timer_end(tncb_ctx* ctx, double ops);    // ops: executed int8 ops (K1
 int ensure_partial(tncb_ctx* ctx, size_t elems);
 size_t k0_partial_elems(int sm_count, const PairPlan& p);
 
+// ---- batched tiny pairs: every independent K0 pair of one tree level in ONE launch (plans with a static layout) ----
+constexpr int kBatchGroups = 8;
+struct CompactLegs { int n; int _pad; long long dim[kBatchGroups]; long long sa[kBatchGroups]; long long sb[kBatchGroups]; };
+struct K0BatchItem {
+  long long offA, offB, offC;   // byte offsets into the plan workspace
+  long long M, N, K;
+  int G, _pad;                  // lanes per output element: the value k0_config picks for the single-pair kernel (bit-identical sums)
+  CompactLegs m, n, k;
+};
+bool k0_batch_eligible(int sm_count, const PairPlan& p);
+int k0_batch_fill(int sm_count, const PairPlan& p, K0BatchItem* item);   // returns the number of 256-thread blocks of the item
+int launch_k0_batch(tncb_ctx* ctx, const K0BatchItem* d_items, const int* d_block_start, int n_items, int total_blocks, char* ws);
+
 int tensor_new(tncb_ctx* ctx, int rank, const uint64_t* dims, tncb_tensor** out);
 } // namespace tncb
 

@@ -467,6 +467,97 @@ static int launch_k0(tncb_ctx* ctx, const PairPlan& P, const double2* A, const d
   return TNCB_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// K0 batch: all independent tiny pairs of one level of the contraction tree in one launch.  Block b looks its pair up
+// by binary search over the prefix of block counts; arithmetic per output element is that of k0_kernel<G> with the G
+// k0_config chooses for the pair (lane i sums k = i, i + G, ...; xor-butterfly over G lanes), so plans with a static
+// layout give bit-identical results to the pair-by-pair executor.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long decomp_c(long long idx, const CompactLegs& L) {
+  long long off = 0;
+  for (int g = L.n - 1; g > 0; --g) {
+    const long long d = L.dim[g], q = idx / d;
+    off += (idx - q * d) * L.sa[g];
+    idx = q;
+  }
+  if (L.n > 0) off += idx * L.sa[0];
+  return off;
+}
+
+__global__ void __launch_bounds__(K0_THREADS)
+k0_batch_kernel(const K0BatchItem* __restrict__ items, const int* __restrict__ block_start, int n_items, char* __restrict__ ws) {
+  int lo = 0, hi = n_items;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(block_start + mid) <= (int)blockIdx.x) lo = mid; else hi = mid;
+  }
+  const K0BatchItem& it = items[lo];
+  const int G = it.G, tid = threadIdx.x;
+  const int lane_g = tid & (G - 1);
+  const long long MN = it.M * it.N;
+  const long long o = (long long)((int)blockIdx.x - __ldg(block_start + lo)) * (K0_THREADS / G) + tid / G;
+  const bool valid = o < MN;
+  long long n = 0, m = 0;
+  if (valid) { n = o / it.M; m = o - n * it.M; }
+  const double2* A = reinterpret_cast<const double2*>(ws + it.offA) + decomp_c(m, it.m);
+  const double2* B = reinterpret_cast<const double2*>(ws + it.offB) + decomp_c(n, it.n);
+  double cr = 0.0, ci = 0.0;
+  if (valid) {
+    for (long long i = lane_g; i < it.K; i += G) {
+      long long oa = 0, ob = 0, idx = i;
+      for (int g = it.k.n - 1; g > 0; --g) {
+        const long long d = it.k.dim[g], q = idx / d, r = idx - q * d;
+        oa += r * it.k.sa[g]; ob += r * it.k.sb[g];
+        idx = q;
+      }
+      if (it.k.n > 0) { oa += idx * it.k.sa[0]; ob += idx * it.k.sb[0]; }
+      const double2 a = A[oa];
+      const double2 b = B[ob];
+      cr = fma(b.x, a.x, cr); cr = fma(-b.y, a.y, cr);
+      ci = fma(b.x, a.y, ci); ci = fma(b.y, a.x, ci);
+    }
+  }
+  for (int d = 16; d > 0; d >>= 1)
+    if (d < G) {   // (G is uniform over the block)
+      cr += __shfl_xor_sync(0xffffffffu, cr, d);
+      ci += __shfl_xor_sync(0xffffffffu, ci, d);
+    }
+  if (valid && lane_g == 0) reinterpret_cast<double2*>(ws + it.offC)[o] = make_double2(cr, ci);
+}
+
+static bool compact_ok(const LegList& L) { return L.n <= kBatchGroups; }
+static void compact_fill(const LegList& L, CompactLegs& C) {
+  C.n = L.n; C._pad = 0;
+  for (int i = 0; i < kBatchGroups; i++) { C.dim[i] = i < L.n ? L.dim[i] : 1; C.sa[i] = i < L.n ? L.sa[i] : 0; C.sb[i] = i < L.n ? L.sb[i] : 0; }
+}
+
+bool k0_batch_eligible(int sm_count, const PairPlan& P) {
+  if (P.kernel_class != 0 || P.M * P.N == 0) return false;
+  if (!compact_ok(P.m) || !compact_ok(P.n) || !compact_ok(P.k)) return false;
+  if (P.K > 4096 || (double)P.M * (double)P.N * (double)P.K > 4194304.0) return false;   // tiny pairs only: no offset tables in the batch kernel
+  int G; long long ksplit, kchunk;
+  k0_config(sm_count, P, &G, &ksplit, &kchunk);
+  return ksplit == 1;
+}
+
+int k0_batch_fill(int sm_count, const PairPlan& P, K0BatchItem* it) {
+  int G; long long ksplit, kchunk;
+  k0_config(sm_count, P, &G, &ksplit, &kchunk);
+  it->M = P.M; it->N = P.N; it->K = P.K; it->G = G; it->_pad = 0;
+  compact_fill(P.m, it->m); compact_fill(P.n, it->n); compact_fill(P.k, it->k);
+  const long long per_block = K0_THREADS / G;
+  return (int)((P.M * P.N + per_block - 1) / per_block);
+}
+
+int launch_k0_batch(tncb_ctx* ctx, const K0BatchItem* d_items, const int* d_block_start, int n_items, int total_blocks, char* ws) {
+  if (n_items <= 0 || total_blocks <= 0) return TNCB_OK;
+  k0_batch_kernel<<<(unsigned)total_blocks, K0_THREADS, 0, ctx->stream>>>(d_items, d_block_start, n_items, ws);
+  ctx->launches++;
+  ctx->engine_count[0] += (uint64_t)n_items;
+  TNCB_CUDA(cudaGetLastError());
+  return TNCB_OK;
+}
+
 template <int BN, int BM, int WN, int WM, int ST, bool BKF, bool AKF, int MINB = 1>
 static int launch_k1_cfg(tncb_ctx* ctx, const K1Args& a) {
   auto kern = k1_kernel<BN, BM, WN, WM, ST, BKF, AKF, MINB>;

@@ -302,20 +302,30 @@ static int execute(tncb_ctx* ctx, const Schedule& S, const tncb_tn* tn, tncb_ten
 
 } // namespace tncb
 
-// Compile once / execute many.  Plans whose steps are all K0 (the launch-bound regime: hundreds of
-// tiny pairs) get a static memory layout and are replayed as ONE CUDA graph: H2D of the staged
-// leaves + every pair kernel, no per-pair host work or launch gaps.
+// Compile once / execute many.  A plan gets a STATIC memory layout (every slot at a fixed offset of one workspace,
+// blocks recycled level by level) unless it has caller-owned device leaves.  Its steps are re-ordered by the level of
+// the contraction tree; all independent tiny (K0) pairs of a level run as ONE batched launch (k0_batch_kernel), the
+// other pairs one by one.  Plans without K1 steps (the launch-bound regime) are additionally captured into a CUDA
+// graph (H2D of the staged leaves + every kernel) and replayed.
 struct tncb_plan {
   tncb::Schedule S;
+  bool is_static = false;            // static layout + level batches available
   bool graphable = false;
-  std::vector<size_t> slot_off;      // byte offset of every slot in the workspace (graph mode)
+  std::vector<size_t> slot_off;      // byte offset of every slot in the workspace
   size_t ws_bytes = 0, scratch_off = 0, scratch_elems = 0, leaf_off = 0;
-  tncb_ctx* ctx = nullptr;           // graph is tied to this context (stream, device)
+  // level structure: steps [level_begin[l], level_begin[l+1]) of S.steps form level l; the batched ones come first
+  std::vector<int> level_begin, level_batched;
+  std::vector<tncb::K0BatchItem> items;            // batched steps of all levels, level by level
+  std::vector<int> block_start;                    // per level: n_batched + 1 prefix entries
+  std::vector<size_t> item_first, bs_first;        // per level: first index into items / block_start
+  void* batch_dev = nullptr; size_t batch_bytes = 0;   // device copy of items + block_start
+  tncb_ctx* ctx = nullptr;           // device state is tied to this context (stream, device)
   void* ws = nullptr;                // arena block
   void* stage = nullptr;             // plan-owned pinned staging of the leaf block
-  cudaGraphExec_t exec = nullptr;
+  bool leaves_resident = false;      // tncb_plan_stage put the leaf block into ws
+  cudaGraphExec_t exec[2] = {nullptr, nullptr};    // [0]: with the H2D of the staged leaves, [1]: leaves resident
   uint64_t kernels_per_run = 0;
-  void* resident = nullptr;          // device copy of the leaf block (tncb_plan_stage), arena block of `resident_bytes`
+  void* resident = nullptr;          // non-static plans: device copy of the leaf block (tncb_plan_stage)
   size_t resident_bytes = 0;
 };
 
@@ -346,30 +356,83 @@ struct OffsetAlloc {
 };
 
 static void plan_static_layout(tncb_plan* P, int sm_count) {
-  const Schedule& S = P->S;
-  P->graphable = !S.steps.empty() && std::getenv("TNCB_NO_GRAPH") == nullptr;
-  for (int k : S.leaf_kind) if (k == TNCB_DATA_DEVICE) P->graphable = false;   // addresses change per call
-  size_t scratch = 0;
-  for (const Step& st : S.steps) {
-    if (st.plan.kernel_class == 1) { P->graphable = false; break; }   // K1/K1' use ctx-owned tables / arena scratch
-    if (st.plan.kernel_class == 0) scratch = std::max(scratch, k0_partial_elems(sm_count, st.plan));
+  Schedule& S = P->S;
+  P->is_static = !S.steps.empty() && std::getenv("TNCB_NO_STATIC") == nullptr;
+  for (int k : S.leaf_kind) if (k == TNCB_DATA_DEVICE) P->is_static = false;   // addresses change per call
+  if (!P->is_static) return;
+  // ---- levels: a step's level is 1 + the deepest level among its operands' producers (leaves: 0) ----
+  std::vector<int> slot_level(S.slots.size(), 0), step_level(S.steps.size(), 0);
+  int n_levels = 0;
+  for (size_t q = 0; q < S.steps.size(); q++) {
+    const Step& st = S.steps[q];
+    step_level[q] = std::max(slot_level[st.a], slot_level[st.b]) + 1;
+    slot_level[st.out] = step_level[q];
+    n_levels = std::max(n_levels, step_level[q]);
   }
-  if (!P->graphable) return;
+  static const bool no_batch = std::getenv("TNCB_NO_BATCH") != nullptr;
+  std::vector<size_t> order(S.steps.size());
+  for (size_t q = 0; q < order.size(); q++) order[q] = q;
+  std::vector<char> batchable(S.steps.size(), 0);
+  for (size_t q = 0; q < S.steps.size(); q++) batchable[q] = !no_batch && k0_batch_eligible(sm_count, S.steps[q].plan);
+  std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) {
+    if (step_level[x] != step_level[y]) return step_level[x] < step_level[y];
+    return batchable[x] > batchable[y];                  // batched pairs first inside a level
+  });
+  std::vector<Step> sorted; sorted.reserve(S.steps.size());
+  std::vector<int> lv; std::vector<char> bt;
+  for (size_t q : order) { sorted.push_back(std::move(S.steps[q])); lv.push_back(step_level[q]); bt.push_back(batchable[q]); }
+  S.steps.swap(sorted);
+  // steps [level_begin[l], level_begin[l+1]) form level l (0-based); step_level counts from 1
+  P->level_begin.assign(n_levels + 1, 0); P->level_batched.assign(n_levels, 0);
+  for (size_t q = 0; q < S.steps.size(); q++) { P->level_begin[lv[q]]++; if (bt[q]) P->level_batched[lv[q] - 1]++; }
+  for (int l = 1; l <= n_levels; l++) P->level_begin[l] += P->level_begin[l - 1];
+  for (int l = 0; l < n_levels; l++) if (P->level_batched[l] < 2) P->level_batched[l] = 0;   // a batch of one is just a launch
+  // ---- layout: outputs of a level are allocated before any operand of that level is released ----
+  size_t scratch = 0;
+  for (const Step& st : S.steps) if (st.plan.kernel_class == 0) scratch = std::max(scratch, k0_partial_elems(sm_count, st.plan));
   OffsetAlloc A;
   P->leaf_off = A.alloc(std::max<size_t>(S.leaf_block_elems * sizeof(double2), 16));
   P->scratch_elems = scratch;
   P->scratch_off = scratch ? A.alloc(scratch * sizeof(double2)) : 0;
   P->slot_off.assign(S.slots.size(), 0);
   std::vector<size_t> sz(S.slots.size(), 0);
-  for (size_t s = 0; s < S.slots.size(); s++)
-    if (S.slots[s].leaf_index >= 0) P->slot_off[s] = P->leaf_off + S.leaf_offset[S.slots[s].leaf_index] * sizeof(double2);
-  for (const Step& st : S.steps) {
-    sz[st.out] = std::max<size_t>(S.slots[st.out].elems * sizeof(double2), 16);
-    P->slot_off[st.out] = A.alloc(sz[st.out]);
-    for (int s : {st.a, st.b}) if (sz[s]) { A.free(P->slot_off[s], sz[s]); sz[s] = 0; }
+  for (size_t s2 = 0; s2 < S.slots.size(); s2++)
+    if (S.slots[s2].leaf_index >= 0) P->slot_off[s2] = P->leaf_off + S.leaf_offset[S.slots[s2].leaf_index] * sizeof(double2);
+  for (int l = 0; l < n_levels; l++) {
+    for (int q = P->level_begin[l]; q < P->level_begin[l + 1]; q++) {
+      const Step& st = S.steps[q];
+      sz[st.out] = std::max<size_t>(S.slots[st.out].elems * sizeof(double2), 16);
+      P->slot_off[st.out] = A.alloc(sz[st.out]);
+    }
+    for (int q = P->level_begin[l]; q < P->level_begin[l + 1]; q++) {
+      const Step& st = S.steps[q];
+      for (int s2 : {st.a, st.b}) if (sz[s2]) { A.free(P->slot_off[s2], sz[s2]); sz[s2] = 0; }
+    }
   }
   P->ws_bytes = A.top;
-  if (P->ws_bytes > ((size_t)1 << 30)) P->graphable = false;   // graphs are for small networks
+  size_t limit = (size_t)64 << 30;
+  if (const char* e = std::getenv("TNCB_PLAN_WS_GB")) limit = (size_t)std::max(1, atoi(e)) << 30;
+  if (P->ws_bytes > limit) { P->is_static = false; return; }
+  // ---- batch descriptors ----
+  P->item_first.assign(n_levels, 0); P->bs_first.assign(n_levels, 0);
+  for (int l = 0; l < n_levels; l++) {
+    P->item_first[l] = P->items.size(); P->bs_first[l] = P->block_start.size();
+    const int nb = P->level_batched[l];
+    if (!nb) continue;
+    int blocks = 0;
+    for (int q = P->level_begin[l]; q < P->level_begin[l] + nb; q++) {
+      const Step& st = S.steps[q];
+      K0BatchItem it{};
+      const int nblk = k0_batch_fill(sm_count, st.plan, &it);
+      it.offA = (long long)P->slot_off[st.a]; it.offB = (long long)P->slot_off[st.b]; it.offC = (long long)P->slot_off[st.out];
+      P->items.push_back(it);
+      P->block_start.push_back(blocks);
+      blocks += nblk;
+    }
+    P->block_start.push_back(blocks);
+  }
+  P->graphable = std::getenv("TNCB_NO_GRAPH") == nullptr && P->ws_bytes <= ((size_t)1 << 30);   // graphs are for small networks
+  for (const Step& st : S.steps) if (st.plan.kernel_class == 1) { P->graphable = false; break; }   // K1/K1' use ctx-owned tables / arena scratch
 }
 
 static int stage_leaves(const Schedule& S, const std::vector<const tncb_tn*>& leaves, std::complex<double>* stage) {
@@ -387,50 +450,98 @@ static int stage_leaves(const Schedule& S, const std::vector<const tncb_tn*>& le
   return TNCB_OK;
 }
 
-static int execute_graph(tncb_ctx* ctx, tncb_plan* P, const tncb_tn* tn, tncb_tensor** out, int* n_out, uint64_t* out_legs) {
+// workspace, pinned staging and the device copy of the batch descriptors (once per plan and context)
+static int plan_device_state(tncb_ctx* ctx, tncb_plan* P) {
+  if (P->ctx && P->ctx != ctx) return fail(TNCB_ERR_INVALID, "plan belongs to another context");
+  if (!P->ctx) { P->ctx = ctx; ctx->plans.push_back(P); }
+  int rc;
+  if (!P->ws && (rc = ctx->arena.alloc(P->ws_bytes, &P->ws))) return rc;
+  const size_t block_bytes = std::max<size_t>(P->S.leaf_block_elems * sizeof(double2), 16);
+  if (!P->stage) TNCB_CUDA(cudaMallocHost(&P->stage, block_bytes));
+  if (!P->batch_dev && !P->items.empty()) {
+    const size_t ib = P->items.size() * sizeof(K0BatchItem), bb = P->block_start.size() * sizeof(int);
+    P->batch_bytes = ib + bb;
+    if ((rc = ctx->arena.alloc(P->batch_bytes, &P->batch_dev))) return rc;
+    TNCB_CUDA(cudaMemcpyAsync(P->batch_dev, P->items.data(), ib, cudaMemcpyHostToDevice, ctx->stream));
+    TNCB_CUDA(cudaMemcpyAsync((char*)P->batch_dev + ib, P->block_start.data(), bb, cudaMemcpyHostToDevice, ctx->stream));
+    TNCB_CUDA(cudaStreamSynchronize(ctx->stream));   // (pageable sources)
+  }
+  return TNCB_OK;
+}
+
+// every kernel of the plan on the ctx stream, level by level
+static int enqueue_static(tncb_ctx* ctx, tncb_plan* P) {
+  const Schedule& S = P->S;
+  char* ws = (char*)P->ws;
+  ctx->partial_override = P->scratch_elems ? (double2*)(ws + P->scratch_off) : nullptr;
+  ctx->partial_override_elems = P->scratch_elems;
+  int rc = TNCB_OK;
+  const K0BatchItem* d_items = (const K0BatchItem*)P->batch_dev;
+  const int* d_bs = (const int*)((char*)P->batch_dev + P->items.size() * sizeof(K0BatchItem));
+  const int n_levels = (int)P->level_batched.size();
+  for (int l = 0; l < n_levels && !rc; l++) {
+    const int nb = P->level_batched[l];
+    if (nb) {
+      const int total_blocks = P->block_start[P->bs_first[l] + nb];
+      rc = launch_k0_batch(ctx, d_items + P->item_first[l], d_bs + P->bs_first[l], nb, total_blocks, ws);
+    }
+    for (int q = P->level_begin[l] + nb; q < P->level_begin[l + 1] && !rc; q++) {
+      const Step& st = S.steps[q];
+      rc = launch_pair(ctx, st.plan, (const double2*)(ws + P->slot_off[st.a]), (const double2*)(ws + P->slot_off[st.b]),
+                       (double2*)(ws + P->slot_off[st.out]));
+    }
+  }
+  ctx->partial_override = nullptr; ctx->partial_override_elems = 0;
+  return rc;
+}
+
+// `tn` == nullptr: run on the leaves that tncb_plan_stage left in the workspace
+static int execute_static(tncb_ctx* ctx, tncb_plan* P, const tncb_tn* tn, tncb_tensor** out, int* n_out, uint64_t* out_legs) {
   const Schedule& S = P->S;
   TNCB_CUDA(cudaSetDevice(ctx->device));
-  std::vector<const tncb_tn*> leaves;
-  collect_leaf_nodes(tn, leaves);
   int rc;
-  if ((rc = validate_leaves(S, leaves))) return rc;
+  std::vector<const tncb_tn*> leaves;
+  if (tn) {
+    collect_leaf_nodes(tn, leaves);
+    if ((rc = validate_leaves(S, leaves))) return rc;
+  } else if (!P->leaves_resident) return fail(TNCB_ERR_INVALID, "tncb_plan_stage has not been called on this plan");
+  if ((rc = plan_device_state(ctx, P))) return rc;
   const size_t block_bytes = std::max<size_t>(S.leaf_block_elems * sizeof(double2), 16);
-  if (!P->exec) {
-    // (re-entered after a failed first call: keep what is already allocated instead of leaking it)
-    if (!P->ctx) { P->ctx = ctx; ctx->plans.push_back(P); }
-    if (!P->ws && (rc = ctx->arena.alloc(P->ws_bytes, &P->ws))) return rc;
-    if (!P->stage) TNCB_CUDA(cudaMallocHost(&P->stage, block_bytes));
-  } else {
-    TNCB_CUDA(cudaStreamSynchronize(ctx->stream));   // the previous replay may still read the staging buffer
-  }
-  if ((rc = stage_leaves(S, leaves, (std::complex<double>*)P->stage))) return rc;
   char* ws = (char*)P->ws;
-  if (!P->exec) {
-    cudaGraph_t graph = nullptr;
-    const uint64_t launches_before = ctx->launches;
-    TNCB_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-    cudaMemcpyAsync(ws + P->leaf_off, P->stage, block_bytes, cudaMemcpyHostToDevice, ctx->stream);
-    ctx->partial_override = P->scratch_elems ? (double2*)(ws + P->scratch_off) : nullptr;
-    ctx->partial_override_elems = P->scratch_elems;
-    rc = TNCB_OK;
-    for (const Step& st : S.steps)
-      if ((rc = launch_pair(ctx, st.plan, (const double2*)(ws + P->slot_off[st.a]), (const double2*)(ws + P->slot_off[st.b]),
-                            (double2*)(ws + P->slot_off[st.out])))) break;
-    ctx->partial_override = nullptr; ctx->partial_override_elems = 0;
-    cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
-    P->kernels_per_run = ctx->launches - launches_before;
-    if (rc) { if (graph) cudaGraphDestroy(graph); ctx->launches = launches_before; return rc; }
-    if (ce != cudaSuccess) { ctx->launches = launches_before; P->graphable = false; return fail(TNCB_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce)); }
-    ce = cudaGraphInstantiate(&P->exec, graph, 0);
-    cudaGraphDestroy(graph);
-    if (ce != cudaSuccess) {   // the plan falls back to the eager executor from now on
-      P->exec = nullptr; P->graphable = false; ctx->launches = launches_before;
-      return fail(TNCB_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(ce));
-    }
-    ctx->launches = launches_before;
+  const int which = tn ? 0 : 1;
+  if (tn) {
+    if (P->exec[0] || P->leaves_resident) TNCB_CUDA(cudaStreamSynchronize(ctx->stream));   // an earlier copy may still read the staging buffer
+    if ((rc = stage_leaves(S, leaves, (std::complex<double>*)P->stage))) return rc;
+    P->leaves_resident = false;     // the workspace copy is about to be overwritten with this call's payloads
   }
-  TNCB_CUDA(cudaGraphLaunch(P->exec, ctx->stream));
-  ctx->launches += P->kernels_per_run;
+  if (P->graphable) {
+    if (!P->exec[which]) {
+      cudaGraph_t graph = nullptr;
+      const uint64_t launches_before = ctx->launches;
+      uint64_t ec_before[8]; for (int i = 0; i < 8; i++) ec_before[i] = ctx->engine_count[i];
+      TNCB_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+      if (tn) cudaMemcpyAsync(ws + P->leaf_off, P->stage, block_bytes, cudaMemcpyHostToDevice, ctx->stream);
+      rc = enqueue_static(ctx, P);
+      cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+      P->kernels_per_run = ctx->launches - launches_before;
+      ctx->launches = launches_before;
+      for (int i = 0; i < 8; i++) ctx->engine_count[i] = ec_before[i];
+      if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+      if (ce != cudaSuccess) { P->graphable = false; return fail(TNCB_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce)); }
+      ce = cudaGraphInstantiate(&P->exec[which], graph, 0);
+      cudaGraphDestroy(graph);
+      if (ce != cudaSuccess) {   // the plan runs eagerly from now on
+        P->exec[which] = nullptr; P->graphable = false;
+        return fail(TNCB_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(ce));
+      }
+    }
+    TNCB_CUDA(cudaGraphLaunch(P->exec[which], ctx->stream));
+    ctx->launches += P->kernels_per_run;
+    ctx->engine_count[0] += S.steps.size();   // (graphable plans hold K0 / K2 pairs only; counted as tiny pairs)
+  } else {
+    if (tn) TNCB_CUDA(cudaMemcpyAsync(ws + P->leaf_off, P->stage, block_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = enqueue_static(ctx, P))) return rc;
+  }
   tncb_tensor* result = nullptr;
   if (S.result_slot >= 0) {
     const SlotMeta& rm = S.slots[S.result_slot];
@@ -470,7 +581,8 @@ int tncb_plan_create(tncb_ctx* ctx, const tncb_tn* tn, const tncb_path* path, tn
 
 int tncb_plan_execute(tncb_ctx* ctx, tncb_plan* plan, const tncb_tn* tn, tncb_tensor** out, int* n_out, uint64_t* out_legs) {
   if (!ctx || !plan || !tn) return tncb::fail(TNCB_ERR_INVALID, "null argument");
-  if (plan->graphable && (plan->ctx == nullptr || plan->ctx == ctx)) return tncb::execute_graph(ctx, plan, tn, out, n_out, out_legs);
+  static const bool trace = std::getenv("TNCB_TRACE") != nullptr;   // per-step times come from the pair-by-pair executor
+  if (plan->is_static && !trace && (plan->ctx == nullptr || plan->ctx == ctx)) return tncb::execute_static(ctx, plan, tn, out, n_out, out_legs);
   return tncb::execute(ctx, plan->S, tn, out, n_out, out_legs);
 }
 
@@ -489,6 +601,15 @@ int tncb_plan_stage(tncb_ctx* ctx, tncb_plan* plan, const tncb_tn* tn) {
   if (rc) return rc;
   const size_t bytes = std::max<size_t>(S.leaf_block_elems * sizeof(double2), 16);
   std::vector<std::complex<double>> host(std::max<size_t>(S.leaf_block_elems, 1));
+  if (plan->is_static) {      // the leaf block lives inside the plan workspace
+    if ((rc = tncb::plan_device_state(ctx, plan))) return rc;
+    TNCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if ((rc = tncb::stage_leaves(S, leaves, (std::complex<double>*)plan->stage))) return rc;
+    TNCB_CUDA(cudaMemcpyAsync((char*)plan->ws + plan->leaf_off, plan->stage, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    TNCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    plan->leaves_resident = true;
+    return TNCB_OK;
+  }
   if ((rc = tncb::stage_leaves(S, leaves, host.data()))) return rc;
   if (!plan->ctx) { plan->ctx = ctx; ctx->plans.push_back(plan); }
   if (!plan->resident) {
@@ -502,6 +623,11 @@ int tncb_plan_stage(tncb_ctx* ctx, tncb_plan* plan, const tncb_tn* tn) {
 
 int tncb_plan_run(tncb_ctx* ctx, tncb_plan* plan, tncb_tensor** out, int* n_out, uint64_t* out_legs) {
   if (!ctx || !plan) return tncb::fail(TNCB_ERR_INVALID, "null argument");
+  static const bool trace = std::getenv("TNCB_TRACE") != nullptr;
+  if (plan->is_static && plan->leaves_resident && plan->ctx == ctx) {
+    if (!trace) return tncb::execute_static(ctx, plan, nullptr, out, n_out, out_legs);
+    return tncb::execute(ctx, plan->S, nullptr, out, n_out, out_legs, (const double2*)((char*)plan->ws + plan->leaf_off));
+  }
   if (!plan->resident || plan->ctx != ctx) return tncb::fail(TNCB_ERR_INVALID, "tncb_plan_stage has not been called on this context");
   return tncb::execute(ctx, plan->S, nullptr, out, n_out, out_legs, (const double2*)plan->resident);
 }
@@ -525,6 +651,7 @@ int tncb_plan_info(const tncb_plan* plan, uint64_t* n_pairs, double* flops, doub
   if (n_kernels) {
     uint64_t k = 0;
     for (const tncb::Step& st : S.steps) k += st.plan.kernel_class == 1 ? 2 : 1;  // (K1: table build + GEMM)
+    for (int nb : plan->level_batched) if (nb) k -= (uint64_t)(nb - 1);            // a batch is one launch
     *n_kernels = k;
   }
   return TNCB_OK;
@@ -537,7 +664,9 @@ void tncb_plan_release_device_state(tncb_plan* plan) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  if (plan->exec) { cudaGraphExecDestroy(plan->exec); plan->exec = nullptr; }
+  for (int i = 0; i < 2; i++) if (plan->exec[i]) { cudaGraphExecDestroy(plan->exec[i]); plan->exec[i] = nullptr; }
+  if (plan->batch_dev) { ctx->arena.free(plan->batch_dev, plan->batch_bytes); plan->batch_dev = nullptr; }
+  plan->leaves_resident = false;
   if (plan->ws) { ctx->arena.free(plan->ws, plan->ws_bytes); plan->ws = nullptr; }
   if (plan->stage) { cudaFreeHost(plan->stage); plan->stage = nullptr; }
   if (plan->resident) { ctx->arena.free(plan->resident, plan->resident_bytes); plan->resident = nullptr; }
