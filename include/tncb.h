@@ -90,7 +90,8 @@ int tncb_ctx_set_tcgen05_engine(tncb_ctx* ctx, int engine);
  * Fewer bits need fewer moduli (= int8 GEMM sweeps): see tncb_tcgen05_bound. */
 int tncb_ctx_set_tolerance(tncb_ctx* ctx, double rel);
 /* Pin the number of moduli (2..20; 0 = derive from the tolerance).  The operand bits then follow from
- * log2(prod m_i) >= a + b + log2(K) + 3; measurement / test aid. */
+ * log2(prod m_i) >= a + b + log2(K) + 3; counts above what 53-bit operands need for the pair's K are clamped to that
+ * (more moduli cannot add accuracy).  Measurement / test aid. */
 int tncb_ctx_set_tcgen05_moduli(tncb_ctx* ctx, int n_moduli);
 /* What K1' would do for contraction length k (no GPU): modulus count, operand bits and the guaranteed factor
  * `bound` with |C - C_exact|[n,m] <= bound * max|b[n,:]| * max|a[m,:]|. */
@@ -150,6 +151,14 @@ int tncb_contract_pair_keep(tncb_ctx* ctx, int n_a, const uint64_t* a_legs, cons
 int tncb_contract_pair_into(tncb_ctx* ctx, int n_a, const uint64_t* a_legs, const tncb_tensor* a,
                             int n_b, const uint64_t* b_legs, const tncb_tensor* b,
                             tncb_tensor* out);
+/* tetra::contract for HOST operands (interleaved complex128, row-major), pipelined and asynchronous: the call enqueues
+ * H2D(a, b) on a copy stream, the pair kernels on the ctx stream and D2H(result) on a second copy stream, then
+ * returns.  Back-to-back calls overlap the upload of pair j+1, the kernels of pair j and the download of pair j-1
+ * (three private sets of device buffers).  host_c receives (b \ a) ++ (a \ b) in row-major order
+ * (tncb_pair_out_legs gives legs and dims).  Pinned host memory is required for the overlap; buffers are valid /
+ * reusable after tncb_ctx_synchronize. */
+int tncb_contract_pair_host(tncb_ctx* ctx, int n_a, const uint64_t* a_legs, const uint64_t* a_dims, const double* host_a,
+                            int n_b, const uint64_t* b_legs, const uint64_t* b_dims, const double* host_b, double* host_c);
 /* Leg algebra only (no GPU): Tensor::symmetric_difference, tensor.rs:463-479.
  * Writes (b\a)++(a\b) and the GEMM view M=|a\b|, N=|b\a|, K=|a&b|. */
 int tncb_pair_out_legs(int n_a, const uint64_t* a_legs, const uint64_t* a_dims,
@@ -236,6 +245,14 @@ int tncb_plan_execute(tncb_ctx* ctx, tncb_plan* plan, const tncb_tn* tn,
  * TNCB_DATA_DEVICE leaves (consumed per call) -> TNCB_ERR_UNSUPPORTED. */
 int tncb_plan_stage(tncb_ctx* ctx, tncb_plan* plan, const tncb_tn* tn);
 int tncb_plan_run(tncb_ctx* ctx, tncb_plan* plan, tncb_tensor** out, int* n_out, uint64_t* out_legs);
+/* Sliced execution (fixing the value of summed legs splits one contraction into independent contractions whose results
+ * add up; the reference's declared future work, book/src/future_work.md:9-11): `plan` is compiled for the sliced
+ * structure, the leaf payloads of all n_slices slice networks are materialised and uploaded ONCE, then
+ * tncb_plan_run_slices contracts slices first, first + stride, ... with no host work per slice and returns their sum
+ * (zeros if the range is empty) -- ranks of a multi-GPU job pass (rank, world) and combine with tncb_comm_allreduce_sum. */
+int tncb_plan_stage_slices(tncb_ctx* ctx, tncb_plan* plan, size_t n_slices, const tncb_tn* const* slice_tns);
+int tncb_plan_run_slices(tncb_ctx* ctx, tncb_plan* plan, size_t first, size_t stride,
+                         tncb_tensor** out_sum, int* n_out, uint64_t* out_legs);
 /* Schedule facts: #pairs, sum 8MNK, sum 16(MK+KN+MN), peak arena bytes, #kernels. */
 int tncb_plan_info(const tncb_plan* plan, uint64_t* n_pairs, double* flops, double* bytes,
                    uint64_t* peak_bytes, uint64_t* n_kernels);

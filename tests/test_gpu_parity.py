@@ -356,6 +356,58 @@ def test_permute_and_conjugate(ctx):
         assert np.array_equal(o.to_numpy(), np.conj(np.transpose(x, perm)))
 
 
+def _permute(ctx, x, perm):
+    import tnc_b200 as tb
+    d = tb.DeviceTensor.from_numpy(ctx, x)
+    out = C.c_void_p()
+    tb.check(ctx._l.tncb_permute(ctx.handle, d.handle, (C.c_int * len(perm))(*perm), C.byref(out)))
+    d.release()
+    return tb.DeviceTensor.adopt(ctx, out).to_numpy()
+
+
+def test_contract_pair_host_pipeline(ctx):
+    """tncb_contract_pair_host: 7 back-to-back asynchronous pairs with different payloads (3 slots are recycled twice)
+    must give exactly the results of the synchronous tncb_contract_pair path."""
+    import torch
+    import tnc_b200 as tb
+    rng = np.random.default_rng(23)
+    a_legs, b_legs = [0, 1, 2, 3], [3, 5, 1, 4]
+    a_dims, b_dims = [6, 16, 5, 32], [32, 7, 16, 9]
+    jobs = []
+    for j in range(7):
+        ta = torch.empty(a_dims, dtype=torch.complex128, pin_memory=True); tb_ = torch.empty(b_dims, dtype=torch.complex128, pin_memory=True)
+        to = torch.empty([7, 9, 6, 5], dtype=torch.complex128, pin_memory=True)
+        ta.numpy()[...] = rand_c(rng, a_dims); tb_.numpy()[...] = rand_c(rng, b_dims)
+        jobs.append((ta, tb_, to))
+    for ta, tb_, to in jobs:
+        tb.contract_pair_host(ctx, a_legs, ta.numpy(), b_legs, tb_.numpy(), to.numpy())
+    ctx.synchronize()
+    for ta, tb_, to in jobs:
+        legs, ref = tb.contract_pair(ctx, a_legs, ta.numpy().copy(), b_legs, tb_.numpy().copy())
+        assert legs == [5, 4, 0, 2] and np.array_equal(to.numpy(), ref)
+
+
+def test_tiled_transpose_k3(ctx):
+    """K3 (tiled transpose through shared memory, Permutor::apply circuit_builder.rs:86-114): bit-exact against
+    numpy.transpose over shapes that exercise full / partial tiles, many dim-2 legs, prime dims, identity and
+    inner-run-preserving permutations, and the statevector-like reversal of 22 qubit legs (8 MiB elements)."""
+    rng = np.random.default_rng(17)
+    cases = [((64, 65), (1, 0)), ((100, 37, 29), (2, 0, 1)), ((100, 37, 29), (1, 2, 0)), ((33, 31, 30, 7), (3, 1, 0, 2)),
+             ((2,) * 14, tuple(reversed(range(14)))), ((2,) * 14, (13, 0, 12, 1, 11, 2, 10, 3, 9, 4, 8, 5, 7, 6)),
+             ((4,) * 7, (6, 5, 0, 1, 2, 3, 4)), ((4,) * 7, (0, 1, 2, 3, 5, 4, 6)), ((3, 5, 7, 11, 13), (4, 2, 0, 3, 1)),
+             ((1024, 3, 128), (2, 1, 0)), ((40, 2, 40, 2, 40), (3, 1, 4, 2, 0)), ((5000, 3), (1, 0)), ((3, 5000), (1, 0)),
+             ((17, 4096), (0, 1))]
+    for shape, perm in cases:
+        x = rand_c(rng, shape)
+        ctx.reset_stats()
+        got = _permute(ctx, x, perm)
+        assert ctx.engine_counts()["permute"] == 1
+        assert np.array_equal(got, np.transpose(x, perm)), (shape, perm)
+    x = rand_c(rng, (2,) * 22)
+    perm = tuple(reversed(range(22)))
+    assert np.array_equal(_permute(ctx, x, perm), np.transpose(x, perm))
+
+
 # ---- full-size C2: size-independent properties --------------------------------------------------
 def test_c2_full_size_properties(ctx):
     """BASELINE config 2: rank-12, dim-4 operands (2^24 elements each), M=N=K=4096, shared legs

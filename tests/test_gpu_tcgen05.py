@@ -170,6 +170,8 @@ def test_tolerance_driven_modulus_count(tc_ctx, K):
 def test_forced_modulus_counts(tc_ctx):
     rng = np.random.default_rng(77)
     prev = None
+    import tnc_b200 as tb
+    assert tb.tcgen05_bound(512, 0.0, 20)["n_moduli"] == tb.tcgen05_bound(512)["n_moduli"] == 16     # clamped to what 53 bits need
     for n in (20, 16, 12, 8, 4):
         _, bd, e = bound_check(tc_ctx, rng, 256, 128, 512, 0.0, n_mod=n)
         assert prev is None or bd["bound"] >= prev

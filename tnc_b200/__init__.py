@@ -206,6 +206,14 @@ def contract_pair_into(ctx: Context, a_legs, da: DeviceTensor, b_legs, db: Devic
                                          len(b_legs), u64_array(b_legs), db.handle, dc.handle))
 
 
+def contract_pair_host(ctx: Context, a_legs, a: np.ndarray, b_legs, b: np.ndarray, out: np.ndarray) -> None:
+    """Pipelined host-buffer pair (tncb_contract_pair_host): asynchronous; `out` (C-contiguous complex128 with
+    prod(out dims) elements, ideally pinned like a and b) is valid after ctx.synchronize()."""
+    check(ctx._l.tncb_contract_pair_host(ctx.handle, len(a_legs), u64_array(a_legs), u64_array(a.shape), a.ctypes.data_as(C.c_void_p),
+                                         len(b_legs), u64_array(b_legs), u64_array(b.shape), b.ctypes.data_as(C.c_void_p),
+                                         out.ctypes.data_as(C.c_void_p)))
+
+
 def upload_into(ctx: Context, host: np.ndarray, dst: DeviceTensor) -> None:
     """Asynchronous H2D of a (pinned) host array into an existing device tensor."""
     check(ctx._l.tncb_tensor_write(ctx.handle, dst.handle, host.ctypes.data_as(C.c_void_p)))

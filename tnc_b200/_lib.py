@@ -84,6 +84,7 @@ SIGNATURES = {
     "tncb_contract_pair": (C.c_int, [C.c_void_p, C.c_int, u64p, C.c_int, u64p, C.c_void_p, C.c_int, u64p, C.c_void_p, vpp]),
     "tncb_contract_pair_keep": (C.c_int, [C.c_void_p, C.c_int, u64p, C.c_void_p, C.c_int, u64p, C.c_void_p, vpp]),
     "tncb_contract_pair_into": (C.c_int, [C.c_void_p, C.c_int, u64p, C.c_void_p, C.c_int, u64p, C.c_void_p, C.c_void_p]),
+    "tncb_contract_pair_host": (C.c_int, [C.c_void_p, C.c_int, u64p, u64p, C.c_void_p, C.c_int, u64p, u64p, C.c_void_p, C.c_void_p]),
     "tncb_pair_out_legs": (C.c_int, [C.c_int, u64p, u64p, C.c_int, u64p, u64p, i32p, u64p, u64p, u64p, u64p, u64p]),
     "tncb_pair_kernel_class": (C.c_int, [C.c_int, u64p, u64p, C.c_int, u64p, u64p]),
     "tncb_permute": (C.c_int, [C.c_void_p, C.c_void_p, i32p, vpp]),
@@ -95,6 +96,8 @@ SIGNATURES = {
     "tncb_plan_execute": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(TncbTn), vpp, i32p, u64p]),
     "tncb_plan_stage": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(TncbTn)]),
     "tncb_plan_run": (C.c_int, [C.c_void_p, C.c_void_p, vpp, i32p, u64p]),
+    "tncb_plan_stage_slices": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.POINTER(TncbTn))]),
+    "tncb_plan_run_slices": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, vpp, i32p, u64p]),
     "tncb_plan_info": (C.c_int, [C.c_void_p, u64p, f64p, f64p, u64p, u64p]),
     "tncb_plan_destroy": (None, [C.c_void_p]),
     "tncb_comm_unique_id": (C.c_int, [C.c_void_p]),

@@ -123,9 +123,11 @@ def communication_path_op_costs(inputs: Sequence[Tensor], path, only_count_ops: 
 # The reference scores partitionings by operation counts (contract_op_cost_tensors); on a B200 the pairs that dominate a
 # partitioned contraction are as often bandwidth-bound (boundary tensors of 2^28 elements) as compute-bound, and the
 # fan-in moves them over NVLink.  `gpu_time_tensors` is a two-roof estimate per pair, measured rates of this repo's
-# kernels (profiles/r02_engine_sweep.jsonl): K1' ~130 TFLOP/s-equivalent for GEMM-like pairs, ~30 TFLOP/s DMMA otherwise,
-# ~5 TB/s of HBM traffic, ~5 us per launch.  Used by tools/plan_partitions.py to choose among candidate partitionings.
-GPU_RATES = {"crt_flops": 130e12, "dmma_flops": 30e12, "hbm_bytes": 5e12, "launch_s": 5e-6, "nvlink_bytes": 6e11, "hop_s": 30e-6}
+# kernels (profiles/r02_engine_sweep.jsonl, profiles/r02_trace_part*.txt): K1' 160 K/(K+600) TFLOP/s-equivalent for GEMM-like
+# pairs (48 at K=256, 74 at 512, 124 at 2048, 140 at 4096: the residue / reconstruction passes do not shrink with K),
+# ~25 TFLOP/s DMMA otherwise, ~5 TB/s of HBM traffic, ~5 us per launch.  Used by tools/plan_partitions.py to choose
+# among candidate partitionings.
+GPU_RATES = {"crt_flops": 160e12, "crt_k_half": 600.0, "dmma_flops": 25e12, "hbm_bytes": 5e12, "launch_s": 5e-6, "nvlink_bytes": 6e11, "hop_s": 30e-6}
 
 
 def gpu_time_tensors(t1: Tensor, t2: Tensor) -> float:
@@ -133,7 +135,7 @@ def gpu_time_tensors(t1: Tensor, t2: Tensor) -> float:
     m, n = (t1 - t2).size(), (t2 - t1).size()
     flops = 8.0 * m * n * k
     crt = m >= 128 and n >= 128 and k >= 256 and m * n * k >= 2.0 ** 28
-    t_math = flops / (GPU_RATES["crt_flops"] if crt else GPU_RATES["dmma_flops"])
+    t_math = flops / (GPU_RATES["crt_flops"] * k / (k + GPU_RATES["crt_k_half"]) if crt else GPU_RATES["dmma_flops"])
     t_mem = 16.0 * (m * k + n * k + m * n) / GPU_RATES["hbm_bytes"]
     return max(t_math, t_mem) + GPU_RATES["launch_s"]
 

@@ -133,36 +133,32 @@ class SlicedNetwork:
         return Tensor.new_composite(out)
 
 
+class SlicedPlan:
+    """Compile + stage once, run many: the sliced contraction with every slice's leaf block resident on the device and
+    the slice loop inside libtncb200 (tncb_plan_stage_slices / tncb_plan_run_slices)."""
+
+    def __init__(self, tn: Tensor, path: ContractionPath, legs: Sequence[int], ctx=None):
+        from .. import default_context
+        from ..tensornetwork.contraction import NetworkPlan
+        self.ctx = ctx or default_context()
+        self.sn = SlicedNetwork(tn, legs)
+        nets = [self.sn.slice(a) for a in self.sn.assignments]
+        self.n_slices = len(nets)
+        self.plan = NetworkPlan(nets[0], path, ctx=self.ctx)
+        self.plan.stage_slices(nets)
+
+    def run(self, rank: int = 0, world: int = 1, allreduce: bool = True) -> Tensor:
+        from .._lib import check
+        total = self.plan.run_slices(rank, world)
+        if world > 1 and allreduce:
+            check(self.ctx._l.tncb_comm_allreduce_sum(self.ctx.handle, total.tensordata.matrix.handle))
+        return total
+
+
 def contract_sliced(tn: Tensor, path: ContractionPath, legs: Sequence[int], ctx=None, rank: int = 0, world: int = 1,
                     allreduce: bool = True) -> Tensor:
-    """Contracts every slice assigned to this rank (round-robin), accumulates on the device and, with
-    world > 1, sums over ranks with one NCCL all-reduce (`tncb_comm_allreduce_sum`; the communicator
-    must have been set up with `dist.init_device_comm`).  One schedule is compiled and re-used."""
-    import ctypes as C
-    from .. import default_context
-    from .._lib import check
-    from ..tensornetwork.contraction import NetworkPlan
-    ctx = ctx or default_context()
-    sn = SlicedNetwork(tn, legs)
-    mine = sn.assignments[rank::world]
-    plan = None
-    total = None
-    for a in mine:
-        stn = sn.slice(a)
-        if plan is None:
-            plan = NetworkPlan(stn, path, ctx=ctx)
-        res = plan.execute(stn)
-        if total is None:
-            total = res
-        else:
-            check(ctx._l.tncb_tensor_add(ctx.handle, total.tensordata.matrix.handle, res.tensordata.matrix.handle))
-    if total is None:   # more ranks than slices: contribute zeros of the right shape
-        stn = sn.slice(sn.assignments[0])
-        plan = NetworkPlan(stn, path, ctx=ctx)
-        total = plan.execute(stn)
-        from .. import DeviceTensor
-        z = DeviceTensor.from_numpy(ctx, np.zeros(total.bond_dims if total.bond_dims else (), dtype=np.complex128))
-        total.set_tensor_data(TensorData.Matrix(z))
-    if world > 1 and allreduce:
-        check(ctx._l.tncb_comm_allreduce_sum(ctx.handle, total.tensordata.matrix.handle))
-    return total
+    """Contracts every slice assigned to this rank (round-robin: slices rank, rank + world, ...), accumulates on the
+    device and, with world > 1, sums over ranks with one NCCL all-reduce (`tncb_comm_allreduce_sum`; the communicator must
+    have been set up with `dist.init_device_comm`).  One schedule is compiled, all slice payloads are uploaded once and
+    the slice loop runs inside the library; `SlicedPlan` keeps that state for repeated runs."""
+    return SlicedPlan(tn, path, legs, ctx).run(rank, world, allreduce)

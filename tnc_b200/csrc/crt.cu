@@ -75,11 +75,14 @@ double crt_log2_product(int n) {
 //   want_bits: integer bits per operand asked for (53 = full mantissa); nmod_force > 0 pins the modulus count.
 void crt_choose(long long K, int want_bits, int nmod_force, int* nmod, int* bits_a, int* bits_b) {
   const double lk = std::log2((double)std::max<long long>(K, 1));
-  int n = nmod_force;
-  if (n <= 0) {
-    n = 2;
-    while (n < CRT_MAX_MOD && crt_log2_product(n) - 1e-9 < 2.0 * want_bits + lk + 3.0) n++;
-  }
+  auto needed = [&](int bits) {
+    int q = 2;
+    while (q < CRT_MAX_MOD && crt_log2_product(q) - 1e-9 < 2.0 * bits + lk + 3.0) q++;
+    return q;
+  };
+  // A forced count is clamped to what 53-bit operands need: more moduli add no accuracy (the operands have no more
+  // bits) but make C'/P a tiny fraction of 1, where the absolute error of the split CRT sum (~2^-75) would show.
+  int n = nmod_force > 0 ? std::min(nmod_force, needed(53)) : needed(want_bits);
   n = std::max(2, std::min(n, CRT_MAX_MOD));
   int tot = (int)std::floor(crt_log2_product(n) - lk - 3.0 - 1e-9);
   tot = std::max(tot, 2);

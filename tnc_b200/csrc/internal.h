@@ -101,6 +101,12 @@ struct tncb_ctx {
   double2* partial_override = nullptr; size_t partial_override_elems = 0;  // set while a plan graph is captured
   // NCCL
   void* nccl_comm = nullptr; int world = 1, rank = 0;
+  // host pipeline (tncb_contract_pair_host): 3 in-flight jobs, each with its own device operands/result and events;
+  // copies run on their own streams so that H2D of pair j+1, the kernels of pair j and D2H of pair j-1 overlap
+  struct HostSlot { void* buf[3] = {nullptr, nullptr, nullptr}; size_t bytes[3] = {0, 0, 0};
+                    cudaEvent_t in_done = nullptr, comp_done = nullptr, out_done = nullptr; bool busy = false; };
+  HostSlot host_slot[3]; uint64_t host_jobs = 0;
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
   // plans that hold device state (graph, workspace) on this context; detached by tncb_ctx_destroy
   std::vector<struct tncb_plan*> plans;
 };

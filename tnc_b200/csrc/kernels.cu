@@ -17,8 +17,25 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: no link dependency, no cost unless a tool is attached
 
 namespace tncb {
+
+// TNCB_NVTX=1: one NVTX range per pairwise contraction ("K1' M=.. N=.. K=..") around its launches, so that a timeline
+// (nsys / ncu --nvtx) shows the path step by step -- the counterpart of the reference's per-contraction flame-graph spans.
+struct NvtxPairRange {
+  bool on;
+  NvtxPairRange(const PairPlan& P) {
+    static const bool enabled = std::getenv("TNCB_NVTX") != nullptr;
+    on = enabled;
+    if (on) {
+      char buf[96];
+      snprintf(buf, sizeof buf, "pair K%d M=%lld N=%lld K=%lld", P.kernel_class, P.M, P.N, P.K);
+      nvtxRangePushA(buf);
+    }
+  }
+  ~NvtxPairRange() { if (on) nvtxRangePop(); }
+};
 
 // ------------------------------------------------------------------------------------------
 // index helpers
@@ -772,9 +789,104 @@ static int launch_k2(tncb_ctx* ctx, const PairPlan& P, const double2* A, const d
 
 int launch_pair(tncb_ctx* ctx, const PairPlan& P, const double2* A, const double2* B, double2* C) {
   if (P.M * P.N == 0) return TNCB_OK;
+  NvtxPairRange nvtx_range(P);
   if (P.kernel_class == 2) return launch_k2(ctx, P, A, B, C);
   if (P.kernel_class == 1) return launch_k1(ctx, P, A, B, C);
   return launch_k0(ctx, P, A, B, C);
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: tiled transpose (Permutor::apply / tetra transpose, builders/circuit_builder.rs:86-114).
+// A tile is a sub-box over a few leg groups, chosen so that it is >= 32 elements long BOTH along the input's fastest
+// index and along the output's fastest index.  The CTA reads the tile in input order (coalesced 512-byte runs), parks it
+// in shared memory and writes it in output order (coalesced again); a one-element pad per 32 keeps the strided
+// shared-memory reads off one bank.  Bound: HBM, 32 bytes of traffic per element.
+// ------------------------------------------------------------------------------------------
+constexpr int K3_MAXT = 12;       // leg groups inside a tile
+constexpr int K3_TILE = 2048;     // elements per tile (32 KB + pad)
+struct K3Args {
+  int nt;                          // tile groups
+  int ext[K3_MAXT];                // tile extent per tile group
+  long long dim[K3_MAXT], sin[K3_MAXT], sout[K3_MAXT];   // full dim, input stride, output stride of the tile groups
+  int in_order[K3_MAXT], out_order[K3_MAXT];              // tile groups sorted by input stride / by output stride (fastest first)
+  int smem_stride[K3_MAXT];        // linear index inside the tile (input order)
+  int tile_elems;
+  int nr;                          // block-index digits: tiles of every tile group + the remaining groups
+  long long rcount[kMaxGroups + K3_MAXT], rin[kMaxGroups + K3_MAXT], rout[kMaxGroups + K3_MAXT];
+  int rtile[kMaxGroups + K3_MAXT]; // >= 0: this digit walks the tiles of tile group rtile (index base += digit * ext)
+};
+
+// Per-launch tables (identical for every tile): element e of the tile in input order -> input offset and packed
+// per-group indices (5 bits each, extents <= 32); element f in output order -> output offset, packed indices and the
+// shared-memory slot.  Built by one tiny kernel so that the copy kernel does no division per element.
+__global__ void k3_tables_kernel(const __grid_constant__ K3Args p, long long* __restrict__ tab) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= p.tile_elems) return;
+  const int te = p.tile_elems;
+  {
+    int rem = e; long long off = 0; unsigned long long pk = 0;
+    for (int k = 0; k < p.nt; k++) {
+      const int g = p.in_order[k], x = p.ext[g], i = rem % x;
+      rem /= x;
+      off += (long long)i * p.sin[g];
+      pk |= (unsigned long long)i << (5 * g);
+    }
+    tab[e] = off; tab[te + e] = (long long)pk;
+  }
+  {
+    int rem = e, sidx = 0; long long off = 0; unsigned long long pk = 0;
+    for (int k = 0; k < p.nt; k++) {
+      const int g = p.out_order[k], x = p.ext[g], i = rem % x;
+      rem /= x;
+      off += (long long)i * p.sout[g];
+      sidx += i * p.smem_stride[g];
+      pk |= (unsigned long long)i << (5 * g);
+    }
+    tab[2 * te + e] = off; tab[3 * te + e] = (long long)pk; tab[4 * te + e] = sidx;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k3_transpose_kernel(const double2* __restrict__ in, double2* __restrict__ out, const __grid_constant__ K3Args p,
+                    const long long* __restrict__ tab) {
+  extern __shared__ __align__(16) unsigned char k3_smem_raw[];
+  double2* tile = reinterpret_cast<double2*>(k3_smem_raw);
+  // block index -> base offsets; room left in every partially tiled group
+  long long b = blockIdx.x, base_in = 0, base_out = 0;
+  int room[K3_MAXT];                                  // valid indices of tile group g in this tile: i < room[g]
+#pragma unroll
+  for (int g = 0; g < K3_MAXT; g++) room[g] = 32;
+  bool partial = false;
+  for (int d = p.nr - 1; d >= 0; --d) {
+    const long long c = p.rcount[d], q = b / c, r = b - q * c;
+    base_in += r * p.rin[d]; base_out += r * p.rout[d];
+    const int g = p.rtile[d];
+    if (g >= 0) {
+      const long long left = p.dim[g] - r * p.ext[g];
+      if (left < p.ext[g]) { partial = true;
+#pragma unroll
+        for (int h = 0; h < K3_MAXT; h++) if (h == g) room[h] = (int)left;
+      }
+    }
+    b = q;
+  }
+  const int te = p.tile_elems;
+  auto inside = [&](unsigned long long pk) {
+    bool ok = true;
+#pragma unroll
+    for (int g = 0; g < K3_MAXT; g++) ok &= (int)((pk >> (5 * g)) & 31) < room[g];
+    return ok;
+  };
+  for (int e = threadIdx.x; e < te; e += 256) {
+    const long long off = __ldg(tab + e);
+    if (!partial || inside((unsigned long long)__ldg(tab + te + e))) tile[e + (e >> 5)] = __ldg(in + base_in + off);
+  }
+  __syncthreads();
+  for (int f = threadIdx.x; f < te; f += 256) {
+    const long long off = __ldg(tab + 2 * te + f);
+    const int sidx = (int)__ldg(tab + 4 * te + f);
+    if (!partial || inside((unsigned long long)__ldg(tab + 3 * te + f))) out[base_out + off] = tile[sidx + (sidx >> 5)];
+  }
 }
 
 int launch_permute(tncb_ctx* ctx, const double2* in, double2* out, int rank,
@@ -794,10 +906,96 @@ int launch_permute(tncb_ctx* ctx, const double2* in, double2* out, int rank,
   }
   L.n = n;
   if (total == 0) return TNCB_OK;
-  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)ctx->sm_count * 16);
-  permute_kernel<<<blocks, 256, 0, ctx->stream>>>(in, out, L, total);
-  ctx->launches++;
   ctx->engine_count[6]++;
+  static const bool no_tiled = std::getenv("TNCB_NO_K3") != nullptr;
+  if (n <= 1 || no_tiled || total < 4096) {   // identity / tiny: the plain gather kernel (already coalesced or negligible)
+    const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)ctx->sm_count * 16);
+    permute_kernel<<<blocks, 256, 0, ctx->stream>>>(in, out, L, total);
+    ctx->launches++;
+    TNCB_CUDA(cudaGetLastError());
+    return TNCB_OK;
+  }
+  // output strides of the groups
+  std::vector<long long> ostr(n);
+  { long long t = 1; for (int g = n - 1; g >= 0; g--) { ostr[g] = t; t *= L.dim[g]; } }
+  // tile extents: walk the groups from the input's fastest index until the run is >= 32, then from the output's
+  std::vector<int> by_in(n), by_out(n);
+  for (int g = 0; g < n; g++) { by_in[g] = g; by_out[g] = n - 1 - g; }          // output order: last group is fastest
+  std::sort(by_in.begin(), by_in.end(), [&](int x, int y) { return L.sa[x] < L.sa[y]; });
+  std::vector<int> ext(n, 1);
+  auto grow = [&](const std::vector<int>& order) {
+    long long run = 1;
+    for (int g : order) {
+      if (run >= 32) break;
+      if (ext[g] > 1) { run *= ext[g]; if (ext[g] < L.dim[g]) break; continue; }    // already (partly) inside the tile
+      const long long want = (32 + run - 1) / run;
+      ext[g] = (int)std::min<long long>(L.dim[g], want);
+      run *= ext[g];
+      if (ext[g] < L.dim[g]) break;        // a partial group ends the contiguous run
+    }
+  };
+  grow(by_in); grow(by_out);
+  {
+    // tiles of a few dozen elements (many dim-2 legs that are fast on both sides) drown in per-CTA overhead: keep adding
+    // groups, alternately from the input-fast and the output-fast side, until a tile holds >= 1024 elements
+    long long te0 = 1;
+    for (int g = 0; g < n; g++) te0 *= ext[g];
+    size_t pi = 0, po = 0; bool turn = false; int used = 0;
+    for (int g = 0; g < n; g++) used += ext[g] > 1;
+    while (te0 < 1024 && used < K3_MAXT && (pi < by_in.size() || po < by_out.size())) {
+      const std::vector<int>& ord = turn ? by_out : by_in;
+      size_t& ptr = turn ? po : pi;
+      turn = !turn;
+      while (ptr < ord.size() && ext[ord[ptr]] >= L.dim[ord[ptr]]) ptr++;     // already full
+      if (ptr >= ord.size()) continue;
+      const int g = ord[ptr];
+      const long long cur = ext[g];
+      const long long factor = std::max<long long>(2, std::min<long long>((1024 + te0 - 1) / te0, K3_TILE / te0));
+      const long long want = std::min<long long>({L.dim[g], (long long)32, cur * factor});
+      if (want <= cur || te0 / cur * want > K3_TILE) { ptr++; continue; }
+      if (cur == 1) used++;
+      te0 = te0 / cur * want; ext[g] = (int)want;
+      if (ext[g] >= L.dim[g] || ext[g] >= 32) ptr++;
+    }
+  }
+  K3Args a{};
+  std::vector<int> tg;                      // groups with an extent > 1 (or the fastest ones even if their dim is small)
+  for (int g = 0; g < n; g++) if (ext[g] > 1) tg.push_back(g);
+  bool plain = (int)tg.size() > K3_MAXT;
+  a.nt = plain ? 0 : (int)tg.size();
+  long long te = 1;
+  for (int k = 0; k < a.nt; k++) { const int g = tg[k]; a.ext[k] = ext[g]; a.dim[k] = L.dim[g]; a.sin[k] = L.sa[g]; a.sout[k] = ostr[g]; te *= ext[g]; }
+  if (plain || te > K3_TILE || te < 64) {   // degenerate tilings: the plain gather kernel
+    const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)ctx->sm_count * 16);
+    permute_kernel<<<blocks, 256, 0, ctx->stream>>>(in, out, L, total);
+    ctx->launches++;
+    TNCB_CUDA(cudaGetLastError());
+    return TNCB_OK;
+  }
+  a.tile_elems = (int)te;
+  std::vector<int> oi(a.nt), oo(a.nt);
+  for (int k = 0; k < a.nt; k++) oi[k] = oo[k] = k;
+  std::sort(oi.begin(), oi.end(), [&](int x, int y) { return a.sin[x] < a.sin[y]; });
+  std::sort(oo.begin(), oo.end(), [&](int x, int y) { return a.sout[x] < a.sout[y]; });
+  { int st = 1; for (int k = 0; k < a.nt; k++) { a.in_order[k] = oi[k]; a.smem_stride[oi[k]] = st; st *= a.ext[oi[k]]; } }
+  for (int k = 0; k < a.nt; k++) a.out_order[k] = oo[k];
+  // block digits: tiles of the tile groups, then every other group
+  long long blocks = 1; a.nr = 0;
+  for (int k = 0; k < a.nt; k++) {
+    const long long tiles = (a.dim[k] + a.ext[k] - 1) / a.ext[k];
+    if (tiles > 1) { a.rcount[a.nr] = tiles; a.rin[a.nr] = a.sin[k] * a.ext[k]; a.rout[a.nr] = a.sout[k] * a.ext[k]; a.rtile[a.nr] = k; a.nr++; blocks *= tiles; }
+  }
+  for (int g = 0; g < n; g++) if (ext[g] == 1) { a.rcount[a.nr] = L.dim[g]; a.rin[a.nr] = L.sa[g]; a.rout[a.nr] = ostr[g]; a.rtile[a.nr] = -1; a.nr++; blocks *= L.dim[g]; }
+  if (blocks > 0x7fffffffLL) return fail(TNCB_ERR_UNSUPPORTED, "permute grid too large");
+  const int smem = (int)((te + te / 32 + 1) * sizeof(double2));
+  static bool attr_done = false;
+  if (!attr_done) { TNCB_CUDA(cudaFuncSetAttribute(k3_transpose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (K3_TILE + K3_TILE / 32 + 1) * (int)sizeof(double2))); attr_done = true; }
+  int rc = ensure_tab(ctx, (size_t)(5 * te));
+  if (rc) return rc;
+  ctx->tab_valid = false;                       // the K1 offset tables living in the same buffer are gone
+  k3_tables_kernel<<<(unsigned)((te + 255) / 256), 256, 0, ctx->stream>>>(a, ctx->tab);
+  k3_transpose_kernel<<<(unsigned)blocks, 256, smem, ctx->stream>>>(in, out, a, ctx->tab);
+  ctx->launches += 2;
   TNCB_CUDA(cudaGetLastError());
   return TNCB_OK;
 }

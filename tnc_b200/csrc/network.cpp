@@ -327,6 +327,8 @@ struct tncb_plan {
   uint64_t kernels_per_run = 0;
   void* resident = nullptr;          // non-static plans: device copy of the leaf block (tncb_plan_stage)
   size_t resident_bytes = 0;
+  void* slices_dev = nullptr;        // tncb_plan_stage_slices: n_slices leaf blocks, back to back
+  size_t n_slices = 0, slices_bytes = 0;
 };
 
 namespace tncb {
@@ -632,6 +634,67 @@ int tncb_plan_run(tncb_ctx* ctx, tncb_plan* plan, tncb_tensor** out, int* n_out,
   return tncb::execute(ctx, plan->S, nullptr, out, n_out, out_legs, (const double2*)plan->resident);
 }
 
+// Sliced execution (the reference's declared future work, book/src/future_work.md:9-11) without host work per slice:
+// `plan` is compiled for the SLICED structure; the leaf blocks of all slice networks are materialised and uploaded
+// once, then tncb_plan_run_slices walks slices first, first+stride, ... : one device-to-device copy of the slice's leaf
+// block (KBs), the plan's kernels (batched / graph as usual), one accumulation kernel.
+int tncb_plan_stage_slices(tncb_ctx* ctx, tncb_plan* plan, size_t n_slices, const tncb_tn* const* slice_tns) {
+  if (!ctx || !plan || !slice_tns || n_slices == 0) return tncb::fail(TNCB_ERR_INVALID, "null argument");
+  if (!plan->is_static) return tncb::fail(TNCB_ERR_UNSUPPORTED, "sliced execution needs a plan with a static layout (no device leaves)");
+  const tncb::Schedule& S = plan->S;
+  TNCB_CUDA(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = tncb::plan_device_state(ctx, plan))) return rc;
+  const size_t block = std::max<size_t>(S.leaf_block_elems, 1);
+  std::vector<std::complex<double>> host(block * n_slices);
+  for (size_t q = 0; q < n_slices; q++) {
+    if (!slice_tns[q]) return tncb::fail(TNCB_ERR_INVALID, "slice network is null");
+    std::vector<const tncb_tn*> leaves;
+    tncb::collect_leaf_nodes(slice_tns[q], leaves);
+    if ((rc = tncb::validate_leaves(S, leaves))) return rc;
+    if ((rc = tncb::stage_leaves(S, leaves, host.data() + q * block))) return rc;
+  }
+  TNCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (plan->slices_dev) { ctx->arena.free(plan->slices_dev, plan->slices_bytes); plan->slices_dev = nullptr; }
+  plan->slices_bytes = host.size() * sizeof(double2);
+  if ((rc = ctx->arena.alloc(plan->slices_bytes, &plan->slices_dev))) return rc;
+  TNCB_CUDA(cudaMemcpyAsync(plan->slices_dev, host.data(), plan->slices_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  TNCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  plan->n_slices = n_slices;
+  return TNCB_OK;
+}
+
+int tncb_plan_run_slices(tncb_ctx* ctx, tncb_plan* plan, size_t first, size_t stride, tncb_tensor** out, int* n_out, uint64_t* out_legs) {
+  if (!ctx || !plan || stride == 0) return tncb::fail(TNCB_ERR_INVALID, "bad argument");
+  if (!plan->slices_dev || plan->ctx != ctx) return tncb::fail(TNCB_ERR_INVALID, "tncb_plan_stage_slices has not been called on this context");
+  const tncb::Schedule& S = plan->S;
+  if (S.result_slot < 0) return tncb::fail(TNCB_ERR_INVALID, "plan has no result");
+  TNCB_CUDA(cudaSetDevice(ctx->device));
+  const tncb::SlotMeta& rm = S.slots[S.result_slot];
+  tncb_tensor* sum = nullptr;
+  int rc = tncb::tensor_new(ctx, (int)rm.dims.size(), rm.dims.data(), &sum);
+  if (rc) return rc;
+  const size_t block_bytes = std::max<size_t>(S.leaf_block_elems, 1) * sizeof(double2);
+  char* ws = (char*)plan->ws;
+  bool any = false;
+  for (size_t q = first; q < plan->n_slices; q += stride) {
+    TNCB_CUDA(cudaMemcpyAsync(ws + plan->leaf_off, (char*)plan->slices_dev + q * block_bytes, block_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    plan->leaves_resident = true;
+    tncb_tensor* part = nullptr;
+    if ((rc = tncb::execute_static(ctx, plan, nullptr, &part, nullptr, nullptr))) { tncb_tensor_free(ctx, sum); return rc; }
+    if (!any) {
+      TNCB_CUDA(cudaMemcpyAsync(sum->ptr, part->ptr, rm.elems * sizeof(double2), cudaMemcpyDeviceToDevice, ctx->stream));
+      any = true;
+    } else if ((rc = tncb::launch_add(ctx, sum->ptr, part->ptr, rm.elems))) { tncb_tensor_free(ctx, part); tncb_tensor_free(ctx, sum); return rc; }
+    tncb_tensor_free(ctx, part);
+  }
+  if (!any) TNCB_CUDA(cudaMemsetAsync(sum->ptr, 0, std::max<size_t>(rm.elems, 1) * sizeof(double2), ctx->stream));   // more ranks than slices
+  if (out) *out = sum; else tncb_tensor_free(ctx, sum);
+  if (n_out) *n_out = (int)rm.legs.size();
+  if (out_legs) for (size_t i = 0; i < rm.legs.size(); i++) out_legs[i] = rm.legs[i];
+  return TNCB_OK;
+}
+
 int tncb_plan_info(const tncb_plan* plan, uint64_t* n_pairs, double* flops, double* bytes, uint64_t* peak_bytes, uint64_t* n_kernels) {
   if (!plan) return tncb::fail(TNCB_ERR_INVALID, "plan is null");
   const tncb::Schedule& S = plan->S;
@@ -666,6 +729,7 @@ void tncb_plan_release_device_state(tncb_plan* plan) {
   cudaStreamSynchronize(ctx->stream);
   for (int i = 0; i < 2; i++) if (plan->exec[i]) { cudaGraphExecDestroy(plan->exec[i]); plan->exec[i] = nullptr; }
   if (plan->batch_dev) { ctx->arena.free(plan->batch_dev, plan->batch_bytes); plan->batch_dev = nullptr; }
+  if (plan->slices_dev) { ctx->arena.free(plan->slices_dev, plan->slices_bytes); plan->slices_dev = nullptr; plan->n_slices = 0; }
   plan->leaves_resident = false;
   if (plan->ws) { ctx->arena.free(plan->ws, plan->ws_bytes); plan->ws = nullptr; }
   if (plan->stage) { cudaFreeHost(plan->stage); plan->stage = nullptr; }

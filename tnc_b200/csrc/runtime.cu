@@ -163,6 +163,14 @@ void tncb_ctx_destroy(tncb_ctx* ctx) {
   if (ctx->stage_host) cudaFreeHost(ctx->stage_host);
   if (ctx->gemm_ev0) { cudaEventDestroy(ctx->gemm_ev0); cudaEventDestroy(ctx->gemm_ev1); }
   for (cudaEvent_t e : ctx->gemm_pool) cudaEventDestroy(e);
+  if (ctx->h2d_stream) {
+    cudaStreamSynchronize(ctx->h2d_stream); cudaStreamSynchronize(ctx->d2h_stream);
+    for (auto& sl : ctx->host_slot) {
+      for (int i = 0; i < 3; i++) if (sl.buf[i]) cudaFree(sl.buf[i]);
+      cudaEventDestroy(sl.in_done); cudaEventDestroy(sl.comp_done); cudaEventDestroy(sl.out_done);
+    }
+    cudaStreamDestroy(ctx->h2d_stream); cudaStreamDestroy(ctx->d2h_stream);
+  }
   ctx->arena.release_all();
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -170,7 +178,63 @@ void tncb_ctx_destroy(tncb_ctx* ctx) {
 
 int tncb_ctx_synchronize(tncb_ctx* ctx) {
   if (!ctx) return fail(TNCB_ERR_INVALID, "ctx is null");
+  TNCB_CUDA(cudaSetDevice(ctx->device));
   TNCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ctx->d2h_stream) {   // results of tncb_contract_pair_host still travelling to the host
+    TNCB_CUDA(cudaStreamSynchronize(ctx->h2d_stream));
+    TNCB_CUDA(cudaStreamSynchronize(ctx->d2h_stream));
+    for (auto& sl : ctx->host_slot) sl.busy = false;
+  }
+  return TNCB_OK;
+}
+
+// tetra::contract for HOST operands, pipelined: the call only enqueues (H2D of a and b on a copy stream, the pair
+// kernels on the ctx stream, D2H of the result on a second copy stream) and returns; with back-to-back calls the upload
+// of pair j+1, the contraction of pair j and the download of pair j-1 overlap (PCIe is full duplex), so the steady-state
+// cost per pair is max(H2D, kernels, D2H) instead of their sum.  Host buffers must be pinned (cudaHostAlloc /
+// torch pin_memory) for the copies to be asynchronous; they may be touched again after tncb_ctx_synchronize.
+int tncb_contract_pair_host(tncb_ctx* ctx, int n_a, const uint64_t* a_legs, const uint64_t* a_dims, const double* host_a,
+                            int n_b, const uint64_t* b_legs, const uint64_t* b_dims, const double* host_b, double* host_c) {
+  if (!ctx || !host_a || !host_b || !host_c) return fail(TNCB_ERR_INVALID, "null argument");
+  TNCB_CUDA(cudaSetDevice(ctx->device));
+  PairPlan P;
+  int rc = plan_pair(n_a, a_legs, a_dims, n_b, b_legs, b_dims, P);
+  if (rc) return rc;
+  size_t ea = 1, eb = 1;
+  for (int i = 0; i < n_a; i++) ea *= a_dims[i];
+  for (int i = 0; i < n_b; i++) eb *= b_dims[i];
+  const size_t need[3] = {std::max<size_t>(ea * 16, 16), std::max<size_t>(eb * 16, 16), std::max<size_t>((size_t)(P.M * P.N) * 16, 16)};
+  if (!ctx->h2d_stream) {
+    TNCB_CUDA(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+    TNCB_CUDA(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+    for (auto& sl : ctx->host_slot) {
+      TNCB_CUDA(cudaEventCreateWithFlags(&sl.in_done, cudaEventDisableTiming));
+      TNCB_CUDA(cudaEventCreateWithFlags(&sl.comp_done, cudaEventDisableTiming));
+      TNCB_CUDA(cudaEventCreateWithFlags(&sl.out_done, cudaEventDisableTiming));
+    }
+  }
+  tncb_ctx::HostSlot& sl = ctx->host_slot[ctx->host_jobs % 3];
+  if (sl.busy) TNCB_CUDA(cudaEventSynchronize(sl.out_done));        // the job that used this slot three calls ago
+  for (int i = 0; i < 3; i++)
+    if (sl.bytes[i] < need[i]) {                                     // private buffers (not the arena: they are touched by three streams)
+      if (sl.buf[i]) TNCB_CUDA(cudaFree(sl.buf[i]));
+      sl.buf[i] = nullptr; sl.bytes[i] = 0;
+      cudaError_t e = cudaMalloc(&sl.buf[i], need[i]);
+      if (e != cudaSuccess) { cudaGetLastError(); return fail(TNCB_ERR_OOM, std::string("cudaMalloc (host pipeline): ") + cudaGetErrorString(e)); }
+      sl.bytes[i] = need[i];
+    }
+  TNCB_CUDA(cudaMemcpyAsync(sl.buf[0], host_a, ea * 16, cudaMemcpyHostToDevice, ctx->h2d_stream));
+  TNCB_CUDA(cudaMemcpyAsync(sl.buf[1], host_b, eb * 16, cudaMemcpyHostToDevice, ctx->h2d_stream));
+  TNCB_CUDA(cudaEventRecord(sl.in_done, ctx->h2d_stream));
+  TNCB_CUDA(cudaStreamWaitEvent(ctx->stream, sl.in_done, 0));
+  if ((rc = launch_pair(ctx, P, (const double2*)sl.buf[0], (const double2*)sl.buf[1], (double2*)sl.buf[2]))) return rc;
+  TNCB_CUDA(cudaEventRecord(sl.comp_done, ctx->stream));
+  TNCB_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, sl.comp_done, 0));
+  TNCB_CUDA(cudaMemcpyAsync(host_c, sl.buf[2], (size_t)(P.M * P.N) * 16, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+  TNCB_CUDA(cudaEventRecord(sl.out_done, ctx->d2h_stream));
+  // the next upload into THIS slot's operands must not overtake these kernels: ordered by out_done (waited above)
+  sl.busy = true;
+  ctx->host_jobs++;
   return TNCB_OK;
 }
 

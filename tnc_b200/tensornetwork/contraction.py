@@ -146,6 +146,22 @@ class NetworkPlan:
         res.set_tensor_data(TensorData.Matrix(dt))
         return res
 
+    def stage_slices(self, slice_tns) -> None:
+        """Materialise + upload the leaf blocks of every slice network once (tncb_plan_stage_slices)."""
+        m = _Marshal()
+        nodes = [m.tn(t) for t in slice_tns]
+        ptrs = (C.POINTER(TncbTn) * len(nodes))(*[C.pointer(n) for n in nodes])
+        check(self.ctx._l.tncb_plan_stage_slices(self.ctx.handle, self.handle, len(nodes), ptrs))
+
+    def run_slices(self, first: int = 0, stride: int = 1) -> Tensor:
+        """Sum of the slices first, first + stride, ... on the device, no host work per slice."""
+        out, n_out, legs = C.c_void_p(), C.c_int(), u64_array([0] * 64)
+        check(self.ctx._l.tncb_plan_run_slices(self.ctx.handle, self.handle, int(first), int(stride), C.byref(out), C.byref(n_out), legs))
+        dt = DeviceTensor.adopt(self.ctx, out)
+        res = Tensor([legs[i] for i in range(n_out.value)], dt.shape)
+        res.set_tensor_data(TensorData.Matrix(dt))
+        return res
+
     def execute(self, tn: Tensor) -> Tensor:
         m = _Marshal()
         c_tn = m.tn(tn)

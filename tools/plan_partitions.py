@@ -56,9 +56,10 @@ def _split_to(tn, partitioning, n):
     from tnc_b200.contractionpath.tree_partition import tree_cut
     from tnc_b200.tensornetwork.tensor import Tensor
     part = list(partitioning)
+    dead = set()                                     # partitions whose tree cannot be bisected (caterpillar root)
     while len(set(part)) < n:
         best_p, best_cost, best_cut = None, -1.0, None
-        for pid in sorted(set(part)):
+        for pid in sorted(set(part) - dead):
             ids = [i for i, q in enumerate(part) if q == pid]
             if len(ids) < 4:
                 continue
@@ -67,10 +68,13 @@ def _split_to(tn, partitioning, n):
             lp = opt.get_best_replace_path()
             cost = contract_path_cost(comp.tensors, lp, False)[0]
             if cost > best_cost:
-                best_p, best_cost, best_cut = pid, cost, (ids, tree_cut(comp, lp, 2)[0])
+                best_p, best_cost, best_cut = pid, cost, (ids, tree_cut(comp, lp, 2, min_leaves=1)[0])
         if best_p is None:
             break
         ids, cut = best_cut
+        if len(set(cut)) < 2:
+            dead.add(best_p)
+            continue
         new_id = max(part) + 1
         for i, c in zip(ids, cut):
             if c == 1:
