@@ -226,7 +226,10 @@ typedef struct tncb_path {
  * stays on the device.  out_legs must have room for *n_out legs (<= 64).
  * TNCB_DATA_DEVICE leaves are consumed atomically: on TNCB_OK every one of them has been freed
  * (the Rust call moves them); on ANY error none has been touched and the caller still owns all of
- * them.  Their storage stays allocated until the whole schedule has been enqueued. */
+ * them.  Their storage stays allocated until the whole schedule has been enqueued.
+ * The second and later calls with the same STRUCTURE (tree, legs, dims, payload kinds, path -- payload values are free)
+ * run through a compiled plan kept in a small per-context cache (at most 4 plans / a quarter of the device memory,
+ * least recently used evicted; TNCB_PLAN_CACHE=0 disables): no schedule construction, tiny pairs batched per level. */
 int tncb_contract_tensor_network(tncb_ctx* ctx, const tncb_tn* tn, const tncb_path* path,
                                  tncb_tensor** out, int* n_out, uint64_t* out_legs);
 

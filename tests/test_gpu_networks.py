@@ -229,3 +229,30 @@ def test_baseline_networks_vs_oracle(built_lib, name, qubits, rounds):
     if name == "C4":
         assert ec["k1_dmma_splitk"] >= 1, ec      # the M=256, N=64, K=2^20 pair
     print(f"{name}: |gpu-cpu|/|cpu| = {abs(got - ref) / abs(ref):.2e} (tcgen05 on), {abs(got_dmma - ref) / abs(ref):.2e} (DMMA only); engines {ec}")
+
+
+def test_direct_calls_reuse_a_cached_plan(built_lib):
+    """tncb_contract_tensor_network compiles a plan on the second sighting of a structure and replays it afterwards
+    (static layout + batched tiny pairs): far fewer launches, results bit-identical to the pair-by-pair executor, other
+    payloads (bitstrings) of the same circuit served by the same plan."""
+    import tnc_b200 as tb
+    from tnc_b200.builders import random_circuit_builder
+    from tnc_b200.tensornetwork import contract_tensor_network
+    c = tb.Context(0)
+    try:
+        def net(bits):
+            return random_circuit_builder(12, 6, 0.5, 0.5, np.random.default_rng(9)).into_amplitude_network(bits)[0]
+        tn = net("0" * 12)
+        path = greedy(tn)
+        c.reset_stats(); a0 = complex(contract_tensor_network(tn, path, ctx=c).to_numpy()); l0 = c.stats()["kernel_launches"]
+        c.reset_stats(); a1 = complex(contract_tensor_network(tn, path, ctx=c).to_numpy()); l1 = c.stats()["kernel_launches"]
+        c.reset_stats(); a2 = complex(contract_tensor_network(tn, path, ctx=c).to_numpy()); l2 = c.stats()["kernel_launches"]
+        assert a0 == a1 == a2
+        assert l0 >= len(path.toplevel) and l2 == l1 < l0 // 3, (l0, l1, l2)
+        for bits in ("1" * 12, "010101010101"):
+            tnb = net(bits)
+            got = complex(contract_tensor_network(tnb, path, ctx=c).to_numpy())
+            ref = complex(orc.contract_tensor_network(to_oracle(tnb), to_opath(path)).data)
+            assert abs(got - ref) <= 1e-12 * abs(ref) + 1e-18
+    finally:
+        c.close()

@@ -48,10 +48,26 @@ def path_cost(tensors: Sequence[Tuple[Sequence[int], Sequence[int]]], path: Cont
     return flops, peak, peak_legs
 
 
-def find_slices(tn: Tensor, path: ContractionPath, min_slices: int = 1, max_peak_elements: Optional[float] = None) -> List[int]:
+def path_time(tensors: Sequence[Tuple[Sequence[int], Sequence[int]]], path: ContractionPath, sliced: Iterable[int] = ()) -> float:
+    """Predicted device seconds of one slice (contraction_cost.gpu_time_tensors per pair): unlike the flop count it
+    sees that halving K of the dominant pair costs the tcgen05 engine efficiency while halving M or N does not."""
+    from ..tensornetwork.tensor import Tensor as _T
+    from .contraction_cost import gpu_time_tensors
+    sl = set(sliced)
+    ts: List[Optional[_T]] = [_T([l for l in legs if l not in sl], [d for l, d in zip(legs, dims) if l not in sl]) for legs, dims in tensors]
+    total = 0.0
+    for (i, j) in path.toplevel:
+        total += gpu_time_tensors(ts[i], ts[j])
+        ts[i], ts[j] = ts[j] ^ ts[i], None
+    return total
+
+
+def find_slices(tn: Tensor, path: ContractionPath, min_slices: int = 1, max_peak_elements: Optional[float] = None,
+                objective: str = "flops") -> List[int]:
     """Greedy slice finder: repeatedly slice the leg of the currently largest intermediate that
-    minimises the total work (slices x flops), until there are at least `min_slices` slices and the
-    largest intermediate has at most `max_peak_elements` elements.  Output legs are never sliced."""
+    minimises the total work (slices x flops, or slices x predicted device time with objective="time"), until there
+    are at least `min_slices` slices and the largest intermediate has at most `max_peak_elements` elements.
+    Output legs are never sliced."""
     leaves = _flat(tn)
     meta = [(t.legs, t.bond_dims) for t in leaves]
     count: Dict[int, int] = {}
@@ -74,6 +90,8 @@ def find_slices(tn: Tensor, path: ContractionPath, min_slices: int = 1, max_peak
         best, best_cost = None, None
         for l in cands:
             f, p, _ = path_cost(meta, path, sliced + [l])
+            if objective == "time":
+                f = path_time(meta, path, sliced + [l])
             cost = (f * n_slices * dim[l], p)
             if best_cost is None or cost < best_cost:
                 best, best_cost = l, cost

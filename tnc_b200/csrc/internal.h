@@ -109,6 +109,9 @@ struct tncb_ctx {
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
   // plans that hold device state (graph, workspace) on this context; detached by tncb_ctx_destroy
   std::vector<struct tncb_plan*> plans;
+  // structure-keyed cache of plans behind tncb_contract_tensor_network (most recently used last)
+  struct CachedPlan { std::vector<uint64_t> key; struct tncb_plan* plan; };
+  std::vector<CachedPlan> plan_cache;
 };
 
 extern "C" void tncb_plan_release_device_state(struct tncb_plan* plan);

@@ -561,9 +561,73 @@ static int execute_static(tncb_ctx* ctx, tncb_plan* P, const tncb_tn* tn, tncb_t
 
 extern "C" {
 
+// Structure key of a (network, path): everything the schedule depends on (tree shape, legs, dims, payload kinds, pairs)
+// and nothing it does not (payload values).  Two calls with equal keys share one compiled plan.
+static void key_tn(const tncb_tn* t, std::vector<uint64_t>& k, bool* cacheable) {
+  k.push_back(0x7e00000000000000ull | (uint64_t)t->n_children);
+  if (t->n_children == 0) {
+    k.push_back(((uint64_t)(uint32_t)t->kind << 32) | (uint32_t)t->rank);
+    if (t->kind == TNCB_DATA_DEVICE) *cacheable = false;       // consumed per call, addresses differ
+    if (t->rank < 0 || t->rank > tncb::kMaxLegs || (t->rank > 0 && (!t->legs || !t->dims))) { *cacheable = false; return; }
+    for (int i = 0; i < t->rank; i++) { k.push_back(t->legs[i]); k.push_back(t->dims[i]); }
+    return;
+  }
+  for (size_t i = 0; i < t->n_children; i++) key_tn(&t->children[i], k, cacheable);
+}
+static void key_path(const tncb_path* p, std::vector<uint64_t>& k) {
+  if (!p) { k.push_back(0x7f00000000000000ull); return; }
+  k.push_back(0x7d00000000000000ull | (uint64_t)p->n_pairs);
+  for (size_t i = 0; i < 2 * p->n_pairs; i++) k.push_back(p->pairs[i]);
+  k.push_back(0x7c00000000000000ull | (uint64_t)p->n_nested);
+  for (size_t i = 0; i < p->n_nested; i++) { k.push_back(p->nested_index[i]); key_path(&p->nested[i], k); }
+}
+
 int tncb_contract_tensor_network(tncb_ctx* ctx, const tncb_tn* tn, const tncb_path* path,
                                  tncb_tensor** out, int* n_out, uint64_t* out_legs) {
   if (!ctx || !tn) return tncb::fail(TNCB_ERR_INVALID, "null argument");
+  // Repeated contractions of the same circuit (other bitstrings, angles, or simply again) hit a small per-context cache
+  // of compiled plans: no schedule construction, static layout, batched tiny pairs.  TNCB_PLAN_CACHE=0 disables it.
+  static const bool cache_on = !(std::getenv("TNCB_PLAN_CACHE") && atoi(std::getenv("TNCB_PLAN_CACHE")) == 0) && std::getenv("TNCB_TRACE") == nullptr;
+  if (cache_on) {
+    std::vector<uint64_t> key;
+    bool cacheable = true;
+    key_tn(tn, key, &cacheable);
+    key_path(path, key);
+    if (cacheable) {
+      auto& cache = ctx->plan_cache;
+      for (size_t i = 0; i < cache.size(); i++)
+        if (cache[i].key == key) {
+          tncb_ctx::CachedPlan hit = std::move(cache[i]);
+          cache.erase(cache.begin() + i);
+          cache.push_back(std::move(hit));                       // most recently used last
+          tncb_plan* pl = cache.back().plan;
+          int rc = tncb::execute_static(ctx, pl, tn, out, n_out, out_legs);
+          if (rc != TNCB_ERR_OOM) return rc;
+          tncb_plan_destroy(pl); cache.pop_back();               // no room for its workspace any more: pair-by-pair path
+          break;
+        }
+      // a second sighting is what earns a plan: remember the key of a miss, compile on the next call with the same key
+      static thread_local std::vector<uint64_t> last_miss;
+      if (last_miss == key) {
+        tncb_plan* pl = nullptr;
+        if (tncb_plan_create(ctx, tn, path, &pl) == TNCB_OK && pl->is_static) {
+          size_t total = 0, free_b = 0, total_b = 0;
+          for (auto& c : cache) total += c.plan->ws_bytes;
+          cudaMemGetInfo(&free_b, &total_b);
+          while (!cache.empty() && (cache.size() >= 4 || total + pl->ws_bytes > total_b / 4)) {   // at most 4 plans / a quarter of the device
+            total -= cache.front().plan->ws_bytes;
+            tncb_plan_destroy(cache.front().plan); cache.erase(cache.begin());
+          }
+          if (pl->ws_bytes <= total_b / 4) {
+            int rc = tncb::execute_static(ctx, pl, tn, out, n_out, out_legs);
+            if (rc == TNCB_OK) { cache.push_back({std::move(key), pl}); last_miss.clear(); return rc; }
+            tncb_plan_destroy(pl);
+            if (rc != TNCB_ERR_OOM) return rc;
+          } else tncb_plan_destroy(pl);
+        } else if (pl) tncb_plan_destroy(pl);
+      } else last_miss = key;
+    }
+  }
   tncb::Schedule S;
   int rc = tncb::build_schedule(tn, path, S);
   if (rc) return rc;

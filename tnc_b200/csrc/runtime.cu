@@ -156,6 +156,8 @@ void tncb_ctx_destroy(tncb_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  for (auto& c : ctx->plan_cache) tncb_plan_destroy(c.plan);                         // the contract_tensor_network plan cache
+  ctx->plan_cache.clear();
   while (!ctx->plans.empty()) tncb_plan_release_device_state(ctx->plans.back());   // plans may outlive the ctx
   tncb_comm_destroy(ctx);
   if (ctx->tab) cudaFree(ctx->tab);

@@ -19,58 +19,92 @@ from .tensordata import TensorData
 _KIND = {"uncontracted": 0, "matrix": 1, "gate": 2, "device": 3}
 
 
+# TncbTn as a numpy record (same layout as the ctypes Structure / the C struct): a composite's children are filled
+# column-wise instead of one ctypes object per leaf (the 36-qubit bench network has 489 leaves per call)
+_TN_DTYPE = np.dtype([("n_children", np.uint64), ("children", np.uint64), ("rank", np.int32), ("legs", np.uint64), ("dims", np.uint64),
+                      ("kind", np.int32), ("host_re_im", np.uint64), ("gate_name", np.uint64), ("gate_angles", np.uint64),
+                      ("n_gate_angles", np.int32), ("gate_adjoint", np.int32), ("device", np.uint64)], align=True)
+assert _TN_DTYPE.itemsize == C.sizeof(TncbTn), "TncbTn layout drifted"
+_GATE_NAMES = {}
+
+
+def _gate_name_ptr(name: str) -> int:
+    buf = _GATE_NAMES.get(name)
+    if buf is None:
+        buf = _GATE_NAMES[name] = C.create_string_buffer(name.encode())     # interned: stays alive for the process
+    return C.addressof(buf)
+
+
 class _Marshal:
-    """Keeps every ctypes buffer alive for the duration of the call."""
+    """Keeps every buffer the C tree points to alive for the duration of the call."""
 
     def __init__(self):
         self.keep: List[object] = []
         self.device_inputs: List[DeviceTensor] = []
 
-    def tn(self, t: Tensor) -> TncbTn:
-        node = TncbTn()
-        if t.is_composite():
-            arr = (TncbTn * len(t.tensors))(*[self.tn(c) for c in t.tensors])
-            self.keep.append(arr)
-            node.n_children = len(t.tensors)
-            node.children = arr
-            node.kind = 0
-            return node
-        legs, dims = u64_array(t.legs), u64_array(t.bond_dims)
+    def _children(self, tensors) -> int:
+        """array of TncbTn for `tensors`; returns its address"""
+        n = len(tensors)
+        rec = np.zeros(n, dtype=_TN_DTYPE)
+        self.keep.append(rec)
+        ranks = [len(t.legs) for t in tensors]
+        tot = sum(ranks)
+        legs = np.fromiter((l for t in tensors for l in t.legs), dtype=np.uint64, count=tot)
+        dims = np.fromiter((d for t in tensors for d in t.bond_dims), dtype=np.uint64, count=tot)
         self.keep += [legs, dims]
-        node.n_children = 0
-        node.rank = len(t.legs)
-        node.legs, node.dims = legs, dims
-        td = t.tensordata
-        if td.kind == "gate":
-            name, angles, adj = td.gate
-            ang = (C.c_double * max(len(angles), 1))(*angles)
-            nm = C.c_char_p(name.encode())
-            self.keep += [ang, nm]
-            node.kind = 2
-            node.gate_name = nm
-            node.gate_angles = ang
-            node.n_gate_angles = len(angles)
-            node.gate_adjoint = int(adj)
-        elif td.kind == "matrix":
-            m = td.matrix
-            if isinstance(m, DeviceTensor):
-                if m.handle is None:   # consumed by an earlier call (the Rust move left TensorData::Uncontracted behind)
-                    raise TncbError(-3, "Cannot convert uncontracted tensor to data (device tensor already consumed)")
-                node.kind = 3
-                node.device = m.handle
-                self.device_inputs.append(m)
-            else:
-                a = np.asarray(m, dtype=np.complex128, order="C")
-                if list(a.shape) != list(t.bond_dims):
-                    a = a.reshape(t.bond_dims)
-                self.keep.append(a)
-                node.kind = 1
-                node.host_re_im = a.ctypes.data_as(C.POINTER(C.c_double))
-        elif td.kind == "file":
-            node.kind = 99  # TensorData::File needs HDF5 -> TNCB_ERR_UNSUPPORTED
-        else:
-            node.kind = 0
-        return node
+        off = np.zeros(n, dtype=np.uint64)
+        if n > 1:
+            np.cumsum(np.asarray(ranks[:-1], dtype=np.uint64), out=off[1:])
+        rec["rank"] = ranks
+        rec["legs"] = legs.ctypes.data + 8 * off
+        rec["dims"] = dims.ctypes.data + 8 * off
+        n_ang = sum(len(t.tensordata.gate[1]) for t in tensors if t.tensordata.kind == "gate")
+        angles = np.zeros(max(n_ang, 1), dtype=np.float64)
+        self.keep.append(angles)
+        apos = 0
+        for i, t in enumerate(tensors):
+            if t.tensors:
+                rec[i]["n_children"] = len(t.tensors)
+                rec[i]["children"] = self._children(t.tensors)
+                rec[i]["rank"] = 0
+                continue
+            td = t.tensordata
+            k = td.kind
+            if k == "gate":
+                name, ang, adj = td.gate
+                r = rec[i]
+                r["kind"] = 2
+                r["gate_name"] = _gate_name_ptr(name)
+                r["gate_adjoint"] = int(adj)
+                if ang:
+                    angles[apos:apos + len(ang)] = ang
+                    r["gate_angles"] = angles.ctypes.data + 8 * apos
+                    r["n_gate_angles"] = len(ang)
+                    apos += len(ang)
+                else:
+                    r["gate_angles"] = angles.ctypes.data
+            elif k == "matrix":
+                m = td.matrix
+                if isinstance(m, DeviceTensor):
+                    if m.handle is None:   # consumed by an earlier call (the Rust move left TensorData::Uncontracted behind)
+                        raise TncbError(-3, "Cannot convert uncontracted tensor to data (device tensor already consumed)")
+                    rec[i]["kind"] = 3
+                    rec[i]["device"] = m.handle.value or 0
+                    self.device_inputs.append(m)
+                else:
+                    arr = np.asarray(m, dtype=np.complex128, order="C")
+                    if list(arr.shape) != list(t.bond_dims):
+                        arr = arr.reshape(t.bond_dims)
+                    self.keep.append(arr)
+                    rec[i]["kind"] = 1
+                    rec[i]["host_re_im"] = arr.ctypes.data
+            elif k == "file":
+                rec[i]["kind"] = 99  # TensorData::File needs HDF5 -> TNCB_ERR_UNSUPPORTED
+        return rec.ctypes.data
+
+    def tn(self, t: Tensor) -> TncbTn:
+        addr = self._children([t])
+        return TncbTn.from_address(addr)
 
     def path(self, p: ContractionPath) -> TncbPath:
         out = TncbPath()
