@@ -87,11 +87,11 @@ def emulate(A, B, n_moduli):
         assert max(np.abs(accr).max(), np.abs(acci).max()) < 2 ** 31
         magic = int(round(2 ** 32 / m))
 
-        def zmod(acc):
-            z = acc - ((acc * magic + (1 << 31)) >> 32) * m
-            z = z - ((z + 128) >> 8) * m
-            assert z.min() >= -128 and z.max() <= 127 and np.all((z - acc) % m == 0)
-            return z.astype(np.float64)
+        def zmod(acc):       # the epilogue of crt_gemm_kernel: __mulhi quotient, offset byte, one wrap
+            z = acc - ((acc * magic) >> 32) * m + 128
+            z = z - (z >> 8) * m
+            assert z.min() >= 0 and z.max() <= 255 and np.all((z - 128 - acc) % m == 0)
+            return (z - 128).astype(np.float64)
         zr, zi = zmod(accr), zmod(acci)
         s1r, s2r, s1i, s2i = s1r + zr * r1[i], s2r + zr * r2[i], s1i + zi * r1[i], s2i + zi * r2[i]
     P = float(math.prod(ms))

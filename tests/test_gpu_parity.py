@@ -298,6 +298,9 @@ def test_network_errors(ctx):
     def leaf(legs):
         t = Tensor(legs, [2] * len(legs)); t.set_tensor_data(TensorData.new_from_data([2] * len(legs), np.ones(2 ** len(legs)))); return t
     tn = lambda: Tensor.new_composite([leaf([0]), leaf([0, 1]), leaf([1])])
+    import gc
+    gc.collect(); ctx.synchronize()
+    live_before = ctx.stats()["arena_live_bytes"]     # (workspaces of plans cached by earlier successful calls stay allocated)
     with pytest.raises(tb.TncbError) as e:   # slot 1 consumed, used again (tensordata.rs:42)
         contract_tensor_network(tn(), path((0, 1), (2, 1)), ctx=ctx)
     assert e.value.status == -3 and "uncontracted" in str(e.value)
@@ -316,7 +319,7 @@ def test_network_errors(ctx):
         contract_tensor_network(Tensor.new_composite([leaf([0]), g]), path((0, 1)), ctx=ctx)
     # the arena must be balanced after failures
     ctx.synchronize()
-    assert ctx.stats()["arena_live_bytes"] == 0
+    assert ctx.stats()["arena_live_bytes"] == live_before
 
 
 def test_single_leaf_and_empty(ctx):

@@ -50,6 +50,8 @@ constexpr int CRT_TILE = CRT_BT * CRT_BKB;      // 16 KB
 constexpr int CRT_STAGES = 3;
 constexpr int CRT_STAGE_BYTES = 4 * CRT_TILE;   // Br, Bi, X (Ar | Ai), Y (-Ai | Ar)
 constexpr int CRT_THREADS = 192;
+constexpr int CRT_STG_ROW = CRT_BT + 16;         // padded row of the epilogue staging tile (bytes)
+constexpr int CRT_STG_BYTES = 32 * CRT_STG_ROW;  // per epilogue warp: 32 rows x 128 residue bytes of one component
 constexpr int CRT_KCHUNK_MAX = 32768;           // 2 * K * 128 * 128 < 2^31 for K <= 2^15
 constexpr int CRT_G = 34;                       // fixed-point bits of the leading CRT weight
 
@@ -138,7 +140,7 @@ constexpr int kExpMin = -1000;              // rows below 2^-1000 keep absolute 
 
 // Row maxima: max over k of max(|re|, |im|) as the BIT PATTERN of a non-negative double (integer max == value
 // max for those; NaN / Inf patterns are the largest, so one non-finite element marks the row).  Same 32 x 128
-// tiling and ROWFAST switch as the residue kernel; one atomicMax per row and CTA.
+// tiling and lane split as the residue kernel; one shared-memory atomicMax per row and warp, one global per row and CTA.
 __device__ __forceinline__ int crt_exp_from_bits(unsigned long long bits) {
   const int field = (int)(bits >> 52) & 0x7ff;        // (sign bit is clear)
   if (field == 0x7ff) return kExpNonFinite;
@@ -146,41 +148,38 @@ __device__ __forceinline__ int crt_exp_from_bits(unsigned long long bits) {
   return max(field - 1022, kExpMin);                   // ilogb(max) + 1: max * 2^-e in [0.5, 1)
 }
 
-template <bool ROWFAST>
+// Element -> thread map of the 32 x 128 operand tile (shared by the row-max and the residue kernel): a warp covers
+// 2^lk consecutive k times 2^(5-lk) consecutive rows, chosen on the host from the operand's strides so that a warp-wide
+// load touches whole contiguous runs (lk = 5: k is the fastest index, lk = 0: the free index is; e.g. lk = 2 when four
+// consecutive k are contiguous and the next-fastest index is the row).
+__device__ __forceinline__ void crt_tile_coord(int e, int lk, int& r, int& k) {
+  const int lane = e & 31, blk = e >> 5;               // blk in [0, 128): 2^(7-lk) k-blocks x 2^lk row-blocks
+  const int kb = blk & ((128 >> lk) - 1), rb = blk >> (7 - lk);
+  k = (kb << lk) + (lane & ((1 << lk) - 1));
+  r = (rb << (5 - lk)) + (lane >> lk);
+}
+
 __global__ void __launch_bounds__(256)
 crt_rowmax_kernel(const double2* __restrict__ src, const long long* __restrict__ off_row, const long long* __restrict__ off_k,
-                  long long rows, long long K, unsigned long long* __restrict__ rowmax) {
+                  long long rows, long long K, int lk, unsigned long long* __restrict__ rowmax) {
   __shared__ unsigned long long s_max[RES_ROWS_C];
   const long long row0 = (long long)blockIdx.x * RES_ROWS_C, k0 = (long long)blockIdx.y * RES_K_C;
   const int tid = threadIdx.x;
   if (tid < RES_ROWS_C) s_max[tid] = 0ull;
   __syncthreads();
-  // one 32 x 128 tile per CTA, 16 independent loads per thread (same element -> thread map as the residue kernel)
-  unsigned long long m[RES_ROWS_C * RES_K_C / 256];
-#pragma unroll
+  // one 32 x 128 tile per CTA, 16 independent loads per thread
+#pragma unroll 4
   for (int it = 0; it < RES_ROWS_C * RES_K_C / 256; it++) {
-    const int e = it * 256 + tid;
-    const int r = ROWFAST ? (e % RES_ROWS_C) : (e / RES_K_C);
-    const int k = ROWFAST ? (e / RES_ROWS_C) : (e % RES_K_C);
-    m[it] = 0ull;
+    int r, k;
+    crt_tile_coord(it * 256 + tid, lk, r, k);
+    unsigned long long m = 0ull;
     if (row0 + r < rows && k0 + k < K) {
       const double2 v = __ldg(src + __ldg(off_row + row0 + r) + __ldg(off_k + k0 + k));
-      m[it] = max((unsigned long long)__double_as_longlong(fabs(v.x)), (unsigned long long)__double_as_longlong(fabs(v.y)));
+      m = max((unsigned long long)__double_as_longlong(fabs(v.x)), (unsigned long long)__double_as_longlong(fabs(v.y)));
     }
-  }
-  if (ROWFAST) {   // a thread's 16 elements belong to ONE row (e % 32 is constant over it)
-    unsigned long long mm = 0ull;
-#pragma unroll
-    for (int it = 0; it < RES_ROWS_C * RES_K_C / 256; it++) mm = max(mm, m[it]);
-    if (mm) atomicMax(&s_max[tid % RES_ROWS_C], mm);
-  } else {         // iteration `it` covers rows 2 it and 2 it + 1: reduce over the 128 threads of each row first
-#pragma unroll
-    for (int it = 0; it < RES_ROWS_C * RES_K_C / 256; it++) {
-      unsigned long long mm = m[it];
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) mm = max(mm, __shfl_xor_sync(0xffffffffu, mm, d));
-      if ((tid & 31) == 0 && mm) atomicMax(&s_max[2 * it + (tid >> 7)], mm);
-    }
+    // lanes with the same row sit 2^lk apart: reduce over the k lanes of the warp, then one shared atomic per row
+    for (int d = 1; d < (1 << lk); d <<= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if ((tid & ((1 << lk) - 1)) == 0 && m) atomicMax(&s_max[r], m);
   }
   __syncthreads();
   if (tid < RES_ROWS_C && row0 + tid < rows && s_max[tid] != 0ull) atomicMax(rowmax + row0 + tid, s_max[tid]);
@@ -192,10 +191,10 @@ crt_rowmax_kernel(const double2* __restrict__ src, const long long* __restrict__
 // planes: [((mod * COMPS + comp) * rowsP + row) * Kp + k];  COMPS == 2: (re, im) -- Bt side,
 // COMPS == 3: (-im, re, im) -- At side.
 constexpr int RES_ROWS = RES_ROWS_C, RES_K = RES_K_C, RES_RS = RES_K + RES_K / 8 + 1;   // padded row stride (elements)
-template <int COMPS, bool ROWFAST>
+template <int COMPS>
 __global__ void __launch_bounds__(256, 3)
 crt_residue_kernel(const double2* __restrict__ src, const long long* __restrict__ off_row, const long long* __restrict__ off_k,
-                   long long rows, long long K, long long rowsP, long long Kp, const unsigned long long* __restrict__ rowmax, int bits,
+                   long long rows, long long K, long long rowsP, long long Kp, const unsigned long long* __restrict__ rowmax, int bits, int lk,
                    const __grid_constant__ CrtTables T, int8_t* __restrict__ planes) {
   extern __shared__ __align__(16) unsigned char res_smem_raw[];
   double2* tile = reinterpret_cast<double2*>(res_smem_raw);
@@ -211,9 +210,8 @@ crt_residue_kernel(const double2* __restrict__ src, const long long* __restrict_
   const double two_a = scalbn(1.0, bits);
 #pragma unroll 4
   for (int it = 0; it < RES_ROWS * RES_K / 256; it++) {
-    const int e = it * 256 + tid;
-    const int r = ROWFAST ? (e % RES_ROWS) : (e / RES_K);
-    const int k = ROWFAST ? (e / RES_ROWS) : (e % RES_K);
+    int r, k;
+    crt_tile_coord(it * 256 + tid, lk, r, k);
     double2 v = make_double2(0.0, 0.0);
     if (row0 + r < rows && k0 + k < K) {
       v = __ldg(src + __ldg(off_row + row0 + r) + __ldg(off_k + k0 + k));
@@ -449,32 +447,56 @@ crt_gemm_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant_
       const CrtItem w = crt_decode(p, item);
       const int buf = f & 1;
       const int m = p.mod[w.mod_i], magic = p.magic[w.mod_i];
-      const long long row = (long long)w.n0 + (int)crank * CRT_BT + q * 32 + lane;
-      int8_t* out_re = p.R + ((long long)((w.mod_i * p.nkc + w.kc) * 2) * p.Np + row) * p.Mp + w.m0;
+      const long long row0 = (long long)w.n0 + (int)crank * CRT_BT + q * 32;     // first of this warp's 32 rows
+      int8_t* out_re = p.R + ((long long)((w.mod_i * p.nkc + w.kc) * 2) * p.Np + row0) * p.Mp + w.m0;
       int8_t* out_im = out_re + (long long)p.Np * p.Mp;
       c_mbar_wait(&tfull_bar[buf], (f >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256);
+      // columns 0..127 real, 128..255 imaginary, 32 at a time; the TMEM load of chunk c+1 is in flight while chunk c is
+      // reduced (tcgen05.wait::ld waits for every outstanding load of the thread, so it sits before the NEXT issue).
+      // A thread owns a ROW of the accumulator, so direct stores would scatter 32 x 16 bytes over 32 lines per
+      // instruction (measured: the epilogue, not the MMA, paced every item with K <= 1024).  The 32 x 128 bytes of one
+      // component are therefore parked in a per-warp shared-memory tile and written out 4 full 128-byte rows at a time.
+      uint8_t* stg = smem + CRT_STAGES * CRT_STAGE_BYTES + (warp - 2) * CRT_STG_BYTES;
+      uint32_t va[32], vb[32];
+      c_tmem_ld32(tbase, va);
 #pragma unroll 1
-      for (int c0 = 0; c0 < 2 * CRT_BT; c0 += 32) {     // columns 0..127 real, 128..255 imaginary
-        uint32_t v[32];
-        c_tmem_ld32(tbase + (uint32_t)c0, v);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        uint32_t wds[8];
+      for (int c0 = 0; c0 < 2 * CRT_BT; c0 += 64) {
 #pragma unroll
-        for (int j = 0; j < 32; j++) {
-          const int a = (int)v[j];
-          // q = round(a / m) within 1/4 (|a| < 2^31, |magic / 2^32 - 1/m| <= 2^-33): |z| <= 0.75 m <= 192
-          const int qq = (int)(((long long)a * magic + 0x80000000LL) >> 32);
-          int z = a - qq * m + 128;
-          z -= (z >> 8) * m;                           // one wrap: the residue as an OFFSET byte z + 128 in [0, 255]
-          constexpr uint32_t sel[4] = {0x3214u, 0x3240u, 0x3410u, 0x4210u};
-          if ((j & 3) == 0) wds[j >> 2] = 0;
-          wds[j >> 2] = __byte_perm(wds[j >> 2], (uint32_t)z, sel[j & 3]);
+        for (int half = 0; half < 2; half++) {
+          uint32_t (&v)[32] = half == 0 ? va : vb;
+          uint32_t (&nx)[32] = half == 0 ? vb : va;
+          const int cc = c0 + 32 * half;
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (cc + 32 < 2 * CRT_BT) c_tmem_ld32(tbase + (uint32_t)(cc + 32), nx);
+          uint32_t wds[8];
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            const int a = (int)v[j];
+            // q = floor(a * magic / 2^32) in [a/m - 1.25, a/m + 0.25] (|a| < 2^31, |magic / 2^32 - 1/m| <= 2^-33), so
+            // z = a - q m + 128 lies in (64, 1.25 m + 128]: one conditional subtraction of m leaves the OFFSET byte
+            // (residue + 128) in [0, 255]
+            int z = a - __mulhi(a, magic) * m + 128;
+            z -= (z >> 8) * m;
+            constexpr uint32_t sel[4] = {0x3214u, 0x3240u, 0x3410u, 0x4210u};
+            if ((j & 3) == 0) wds[j >> 2] = 0;
+            wds[j >> 2] = __byte_perm(wds[j >> 2], (uint32_t)z, sel[j & 3]);
+          }
+          uint8_t* srow = stg + lane * CRT_STG_ROW + (cc & (CRT_BT - 1));
+          *reinterpret_cast<uint4*>(srow) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+          *reinterpret_cast<uint4*>(srow + 16) = make_uint4(wds[4], wds[5], wds[6], wds[7]);
+          if ((cc & (CRT_BT - 1)) == CRT_BT - 32) {       // a component (128 columns) is complete
+            __syncwarp();
+            int8_t* dst = cc < CRT_BT ? out_re : out_im;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+              const int r = i * 4 + (lane >> 3), c16 = (lane & 7) * 16;
+              *reinterpret_cast<uint4*>(dst + (long long)r * p.Mp + c16) = *reinterpret_cast<const uint4*>(stg + r * CRT_STG_ROW + c16);
+            }
+            __syncwarp();
+          }
         }
-        int8_t* dst = (c0 < CRT_BT ? out_re + c0 : out_im + (c0 - CRT_BT));
-        *reinterpret_cast<uint4*>(dst) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
-        *reinterpret_cast<uint4*>(dst + 16) = make_uint4(wds[4], wds[5], wds[6], wds[7]);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -651,19 +673,25 @@ int launch_k1_crt(tncb_ctx* ctx, const PairPlan& P, const double2* A, const doub
   unsigned long long* max_m = max_n + pn;
 
   static bool attr_done = false;
-  const int smem_gemm = CRT_STAGES * CRT_STAGE_BYTES + 1024;
+  const int smem_gemm = CRT_STAGES * CRT_STAGE_BYTES + 4 * CRT_STG_BYTES + 1024;
   const int smem_res = RES_ROWS * RES_RS * (int)sizeof(double2);
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(crt_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_gemm);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(crt_residue_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_res);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(crt_residue_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_res);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(crt_residue_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_res);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(crt_residue_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_res);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(crt_residue_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_res);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(crt_residue_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_res);
     if (e != cudaSuccess) { cleanup(); return fail(TNCB_ERR_CUDA, cudaGetErrorString(e)); }
     attr_done = true;
   }
-  // rows are "fast" when stepping the free index moves less far in memory than stepping k
-  const bool b_rowfast = !P.b_kfast, a_rowfast = !P.a_kfast;
+  // lanes of a warp: 2^lk along k, the rest along rows -- as many k lanes as the operand's fastest K leg is long when k is
+  // the fastest index (stride 1), otherwise as many row lanes as the fastest free leg is long
+  auto lane_split = [](const LegList& kl, bool k_is_b, const LegList& fl) {
+    auto p2 = [](long long d) { int b = 0; while ((2LL << b) <= d && b < 5) b++; return b; };
+    const long long ks = kl.n ? (k_is_b ? kl.sb[kl.n - 1] : kl.sa[kl.n - 1]) : (1LL << 62);
+    const long long fs = fl.n ? fl.sa[fl.n - 1] : (1LL << 62);
+    if (ks <= fs) return kl.n ? p2(kl.dim[kl.n - 1]) : 0;          // k fastest
+    return 5 - (fl.n ? p2(fl.dim[fl.n - 1]) : 5);                   // rows fastest
+  };
+  const int lk_b = lane_split(P.k, true, P.n), lk_a = lane_split(P.k, false, P.m);
   ctx->last_int8_ops = 0.0; ctx->last_nmod = nmod;
   bool timed = false;
 
@@ -675,10 +703,8 @@ int launch_k1_crt(tncb_ctx* ctx, const PairPlan& P, const double2* A, const doub
     cudaMemsetAsync(max_n, 0, (size_t)nrows * sizeof(unsigned long long), st);
     {
       dim3 g((unsigned)((nrows + RES_ROWS - 1) / RES_ROWS), (unsigned)(Kp / RES_K));
-      if (b_rowfast) crt_rowmax_kernel<true><<<g, 256, 0, st>>>(B, offBn + n0, offBk, nrows, P.K, max_n);
-      else crt_rowmax_kernel<false><<<g, 256, 0, st>>>(B, offBn + n0, offBk, nrows, P.K, max_n);
-      if (b_rowfast) crt_residue_kernel<2, true><<<g, 256, smem_res, st>>>(B, offBn + n0, offBk, nrows, P.K, Np, Kp, max_n, bits_b, T, (int8_t*)pb);
-      else crt_residue_kernel<2, false><<<g, 256, smem_res, st>>>(B, offBn + n0, offBk, nrows, P.K, Np, Kp, max_n, bits_b, T, (int8_t*)pb);
+      crt_rowmax_kernel<<<g, 256, 0, st>>>(B, offBn + n0, offBk, nrows, P.K, lk_b, max_n);
+      crt_residue_kernel<2><<<g, 256, smem_res, st>>>(B, offBn + n0, offBk, nrows, P.K, Np, Kp, max_n, bits_b, lk_b, T, (int8_t*)pb);
     }
     ctx->launches += 2;
     CUtensorMap mapB;
@@ -690,10 +716,8 @@ int launch_k1_crt(tncb_ctx* ctx, const PairPlan& P, const double2* A, const doub
       cudaMemsetAsync(max_m, 0, (size_t)mcols * sizeof(unsigned long long), st);
       {
         dim3 g((unsigned)((mcols + RES_ROWS - 1) / RES_ROWS), (unsigned)(Kp / RES_K));
-        if (a_rowfast) crt_rowmax_kernel<true><<<g, 256, 0, st>>>(A, offAm + m0, offAk, mcols, P.K, max_m);
-        else crt_rowmax_kernel<false><<<g, 256, 0, st>>>(A, offAm + m0, offAk, mcols, P.K, max_m);
-        if (a_rowfast) crt_residue_kernel<3, true><<<g, 256, smem_res, st>>>(A, offAm + m0, offAk, mcols, P.K, Mp, Kp, max_m, bits_a, T, (int8_t*)pa);
-        else crt_residue_kernel<3, false><<<g, 256, smem_res, st>>>(A, offAm + m0, offAk, mcols, P.K, Mp, Kp, max_m, bits_a, T, (int8_t*)pa);
+        crt_rowmax_kernel<<<g, 256, 0, st>>>(A, offAm + m0, offAk, mcols, P.K, lk_a, max_m);
+        crt_residue_kernel<3><<<g, 256, smem_res, st>>>(A, offAm + m0, offAk, mcols, P.K, Mp, Kp, max_m, bits_a, lk_a, T, (int8_t*)pa);
       }
       ctx->launches += 2;
       CUtensorMap mapA;
