@@ -100,6 +100,10 @@ def test_tcgen05_permuted_circuit_like(tc_ctx):
     # shared legs leading in a, trailing in b: both loader modes (row-fast / k-fast) of the preparation kernels
     check(tc_ctx, rng, [0, 1, 2, 3], [16, 16, 16, 16], [4, 5, 0, 1], [16, 16, 16, 16])
     check(tc_ctx, rng, [2, 3, 0, 1], [16, 16, 16, 16], [0, 1, 4, 5], [16, 16, 16, 16])
+    # C2 in small: dim-4 legs, shared legs interleaved with the free ones in both operands (M = N = K = 256): the warp
+    # lanes of the preparation kernels are split 4 along k x 8 along rows (a) and 8 x 4 (b)
+    check(tc_ctx, rng, list(range(8)), [4] * 8, [7, 8, 5, 9, 3, 10, 1, 11], [4] * 8)
+    check(tc_ctx, rng, [0, 1, 2], [160, 64, 48], [2, 3, 1], [48, 130, 64])       # fastest K leg of a is 48 long (lk = 5), of b 64
 
 
 def test_tcgen05_row_scaling(tc_ctx):

@@ -28,8 +28,9 @@
 //   warp 0  TMA producer (cp.async.bulk.tensor 2D, SWIZZLE_128B, 3 stages x 64 KB)
 //   warp 1  (leader CTA) single-thread tcgen05.mma issuer: 2 UMMAs (M=256 N=256 K=32) per 32-byte K step,
 //           Br x [Ar;Ai]^T and Bi x [-Ai;Ar]^T into one 256-column accumulator (cols 0-127 re, 128-255 im)
-//   warps 2-5 epilogue: tcgen05.ld -> (acc mod m_i) -> int8 -> global; TMEM holds two accumulators, so the
-//           epilogue of item j overlaps the MMAs of item j+1.
+//   warps 2-9 epilogue (two per TMEM lane quarter: real / imaginary columns): tcgen05.ld -> (acc mod m_i) -> byte ->
+//           shared-memory staging -> coalesced global stores; TMEM holds two accumulators, so the epilogue of item j
+//           overlaps the MMAs of item j+1.
 #include "internal.h"
 #include <cuda.h>
 #include <algorithm>
@@ -49,8 +50,8 @@ constexpr int CRT_BKB = 128;       // K bytes per stage row (one 128-byte swizzl
 constexpr int CRT_TILE = CRT_BT * CRT_BKB;      // 16 KB
 constexpr int CRT_STAGES = 3;
 constexpr int CRT_STAGE_BYTES = 4 * CRT_TILE;   // Br, Bi, X (Ar | Ai), Y (-Ai | Ar)
-constexpr int CRT_THREADS = 192;
-constexpr int CRT_STG_ROW = CRT_BT + 16;         // padded row of the epilogue staging tile (bytes)
+constexpr int CRT_THREADS = 320;                // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
+constexpr int CRT_STG_ROW = CRT_BT;              // row of the epilogue staging tile (bytes; 16-byte chunks XOR-swizzled by row)
 constexpr int CRT_STG_BYTES = 32 * CRT_STG_ROW;  // per epilogue warp: 32 rows x 128 residue bytes of one component
 constexpr int CRT_KCHUNK_MAX = 32768;           // 2 * K * 128 * 128 < 2^31 for K <= 2^15
 constexpr int CRT_G = 34;                       // fixed-point bits of the leading CRT weight
@@ -167,7 +168,10 @@ crt_rowmax_kernel(const double2* __restrict__ src, const long long* __restrict__
   const int tid = threadIdx.x;
   if (tid < RES_ROWS_C) s_max[tid] = 0ull;
   __syncthreads();
-  // one 32 x 128 tile per CTA, 16 independent loads per thread
+  // one 32 x 128 tile per CTA, 16 independent loads per thread; a thread's row changes at most 2^lk times over the
+  // iterations (never for lk = 0), so its running maximum is flushed to shared memory only when the row changes
+  int cur_r = -1;
+  unsigned long long cur_m = 0ull;
 #pragma unroll 4
   for (int it = 0; it < RES_ROWS_C * RES_K_C / 256; it++) {
     int r, k;
@@ -177,10 +181,15 @@ crt_rowmax_kernel(const double2* __restrict__ src, const long long* __restrict__
       const double2 v = __ldg(src + __ldg(off_row + row0 + r) + __ldg(off_k + k0 + k));
       m = max((unsigned long long)__double_as_longlong(fabs(v.x)), (unsigned long long)__double_as_longlong(fabs(v.y)));
     }
-    // lanes with the same row sit 2^lk apart: reduce over the k lanes of the warp, then one shared atomic per row
+    // lanes with the same row sit next to each other (2^lk of them): reduce over them, lane 0 of the group keeps the result
     for (int d = 1; d < (1 << lk); d <<= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
-    if ((tid & ((1 << lk) - 1)) == 0 && m) atomicMax(&s_max[r], m);
+    if (r != cur_r) {
+      if (cur_m && (tid & ((1 << lk) - 1)) == 0) atomicMax(&s_max[cur_r], cur_m);
+      cur_r = r; cur_m = 0ull;
+    }
+    cur_m = max(cur_m, m);
   }
+  if (cur_m && (tid & ((1 << lk) - 1)) == 0) atomicMax(&s_max[cur_r], cur_m);
   __syncthreads();
   if (tid < RES_ROWS_C && row0 + tid < rows && s_max[tid] != 0ull) atomicMax(rowmax + row0 + tid, s_max[tid]);
 }
@@ -313,10 +322,14 @@ __device__ __forceinline__ void c_commit_2sm(uint64_t* bar) {   // arrives on `b
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(c_smem(bar)), "h"((uint16_t)3) : "memory");
 }
-__device__ __forceinline__ void c_mbar_arrive_cta(uint64_t* bar, uint32_t cta) {   // arrive on `bar` of cluster CTA `cta`
+// arrive on `bar` of cluster CTA `cta`.  Default semantics (release at CTA scope), NOT .release.cluster: the only thing
+// the waiter depends on is that this warp's TMEM reads are done (tcgen05.wait::ld + tcgen05.fence::before_thread_sync);
+// a cluster-scope release compiles to MEMBAR.ALL.GPU + ERRBAR and stalls until every residue byte this warp just stored
+// has reached L2 -- 2-3 thousand cycles per item, which paced all short-K items (ncu: top stall of the kernel).
+__device__ __forceinline__ void c_mbar_arrive_cta(uint64_t* bar, uint32_t cta) {
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(c_smem(bar)), "r"(cta));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 __device__ __forceinline__ void c_tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -372,7 +385,7 @@ crt_gemm_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant_
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < CRT_STAGES; s++) { c_mbar_init(&full_bar[s], 1); c_mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; b++) { c_mbar_init(&tfull_bar[b], 1); c_mbar_init(&tempty_bar[b], 8); }
+    for (int b = 0; b < 2; b++) { c_mbar_init(&tfull_bar[b], 1); c_mbar_init(&tempty_bar[b], 16); }   // 8 epilogue warps x 2 CTAs
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {   // both CTAs, same warp id, same smem destination
@@ -441,63 +454,58 @@ crt_gemm_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant_
     }
   } else if (warp >= 2) {
     // ================= epilogue (both CTAs; own 128 rows): acc mod m_i -> one (offset) byte =================
-    const int q = warp & 3;     // TMEM lane quarter this warp may read
+    // Eight warps: warp w reads TMEM lanes 32 (w % 4) ..., warps 2-5 take the real columns 0-127, warps 6-9 the imaginary
+    // columns 128-255.  Two warps per scheduler hide each other's dependency stalls and keep all four TMEM read ports busy
+    // (ncu r02 with four warps: issue slots 35 % busy, the epilogue -- not the MMA -- paced every item with K <= 1024).
+    const int q = warp & 3;              // TMEM lane quarter this warp may read
+    const int comp = (warp - 2) >> 2;    // 0: real, 1: imaginary
     int f = 0;
     for (int item = cluster_id; item < p.total_items; item += n_clusters, f++) {
       const CrtItem w = crt_decode(p, item);
       const int buf = f & 1;
       const int m = p.mod[w.mod_i], magic = p.magic[w.mod_i];
       const long long row0 = (long long)w.n0 + (int)crank * CRT_BT + q * 32;     // first of this warp's 32 rows
-      int8_t* out_re = p.R + ((long long)((w.mod_i * p.nkc + w.kc) * 2) * p.Np + row0) * p.Mp + w.m0;
-      int8_t* out_im = out_re + (long long)p.Np * p.Mp;
+      int8_t* dst = p.R + ((long long)((w.mod_i * p.nkc + w.kc) * 2 + comp) * p.Np + row0) * p.Mp + w.m0;
       c_mbar_wait(&tfull_bar[buf], (f >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256);
-      // columns 0..127 real, 128..255 imaginary, 32 at a time; the TMEM load of chunk c+1 is in flight while chunk c is
-      // reduced (tcgen05.wait::ld waits for every outstanding load of the thread, so it sits before the NEXT issue).
-      // A thread owns a ROW of the accumulator, so direct stores would scatter 32 x 16 bytes over 32 lines per
-      // instruction (measured: the epilogue, not the MMA, paced every item with K <= 1024).  The 32 x 128 bytes of one
-      // component are therefore parked in a per-warp shared-memory tile and written out 4 full 128-byte rows at a time.
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + comp * CRT_BT);
+      // 32 columns at a time; the TMEM load of chunk c+1 is in flight while chunk c is reduced (tcgen05.wait::ld waits for
+      // every outstanding load of the thread, so it sits before the NEXT issue).  A thread owns a ROW of the accumulator,
+      // so direct stores would scatter 32 x 16 bytes over 32 lines per instruction: the 32 x 128 bytes are parked in a
+      // per-warp shared-memory tile (16-byte chunks XOR-swizzled by row) and written out 4 full 128-byte rows at a time.
       uint8_t* stg = smem + CRT_STAGES * CRT_STAGE_BYTES + (warp - 2) * CRT_STG_BYTES;
       uint32_t va[32], vb[32];
       c_tmem_ld32(tbase, va);
-#pragma unroll 1
-      for (int c0 = 0; c0 < 2 * CRT_BT; c0 += 64) {
 #pragma unroll
-        for (int half = 0; half < 2; half++) {
-          uint32_t (&v)[32] = half == 0 ? va : vb;
-          uint32_t (&nx)[32] = half == 0 ? vb : va;
-          const int cc = c0 + 32 * half;
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (cc + 32 < 2 * CRT_BT) c_tmem_ld32(tbase + (uint32_t)(cc + 32), nx);
-          uint32_t wds[8];
+      for (int ch = 0; ch < 4; ch++) {
+        uint32_t (&v)[32] = (ch & 1) == 0 ? va : vb;
+        uint32_t (&nx)[32] = (ch & 1) == 0 ? vb : va;
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (ch < 3) c_tmem_ld32(tbase + (uint32_t)(32 * (ch + 1)), nx);
+        uint32_t wds[8];
 #pragma unroll
-          for (int j = 0; j < 32; j++) {
-            const int a = (int)v[j];
-            // q = floor(a * magic / 2^32) in [a/m - 1.25, a/m + 0.25] (|a| < 2^31, |magic / 2^32 - 1/m| <= 2^-33), so
-            // z = a - q m + 128 lies in (64, 1.25 m + 128]: one conditional subtraction of m leaves the OFFSET byte
-            // (residue + 128) in [0, 255]
-            int z = a - __mulhi(a, magic) * m + 128;
-            z -= (z >> 8) * m;
-            constexpr uint32_t sel[4] = {0x3214u, 0x3240u, 0x3410u, 0x4210u};
-            if ((j & 3) == 0) wds[j >> 2] = 0;
-            wds[j >> 2] = __byte_perm(wds[j >> 2], (uint32_t)z, sel[j & 3]);
-          }
-          uint8_t* srow = stg + lane * CRT_STG_ROW + (cc & (CRT_BT - 1));
-          *reinterpret_cast<uint4*>(srow) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
-          *reinterpret_cast<uint4*>(srow + 16) = make_uint4(wds[4], wds[5], wds[6], wds[7]);
-          if ((cc & (CRT_BT - 1)) == CRT_BT - 32) {       // a component (128 columns) is complete
-            __syncwarp();
-            int8_t* dst = cc < CRT_BT ? out_re : out_im;
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-              const int r = i * 4 + (lane >> 3), c16 = (lane & 7) * 16;
-              *reinterpret_cast<uint4*>(dst + (long long)r * p.Mp + c16) = *reinterpret_cast<const uint4*>(stg + r * CRT_STG_ROW + c16);
-            }
-            __syncwarp();
-          }
+        for (int j = 0; j < 32; j++) {
+          const int a = (int)v[j];
+          // q = floor(a * magic / 2^32) in [a/m - 1.25, a/m + 0.25] (|a| < 2^31, |magic / 2^32 - 1/m| <= 2^-33), so
+          // z = a - q m + 128 lies in (64, 1.25 m + 128]: one conditional subtraction of m leaves the OFFSET byte
+          // (residue + 128) in [0, 255]
+          int z = a - __mulhi(a, magic) * m + 128;
+          z -= (z >> 8) * m;
+          constexpr uint32_t sel[4] = {0x3214u, 0x3240u, 0x3410u, 0x4210u};
+          if ((j & 3) == 0) wds[j >> 2] = 0;
+          wds[j >> 2] = __byte_perm(wds[j >> 2], (uint32_t)z, sel[j & 3]);
         }
+        uint8_t* srow = stg + lane * CRT_STG_ROW;
+        *reinterpret_cast<uint4*>(srow + (((2 * ch) ^ (lane & 7)) << 4)) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+        *reinterpret_cast<uint4*>(srow + (((2 * ch + 1) ^ (lane & 7)) << 4)) = make_uint4(wds[4], wds[5], wds[6], wds[7]);
       }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int r = i * 4 + (lane >> 3), c16 = lane & 7;
+        *reinterpret_cast<uint4*>(dst + (long long)r * p.Mp + c16 * 16) = *reinterpret_cast<const uint4*>(stg + r * CRT_STG_ROW + ((c16 ^ (r & 7)) << 4));
+      }
+      __syncwarp();
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) c_mbar_arrive_cta(&tempty_bar[buf], 0);   // the leader's MMA issuer waits for all 8 epilogue warps
@@ -520,49 +528,45 @@ struct CrtReconArgs {
   int nkc;
 };
 
-// one thread: 8 consecutive m of one row n.  No conversion-pipe instruction in the inner loop: a residue byte u = y + 128
-// becomes the double 2^52 + u by a byte permute into the low mantissa word, one DADD removes 2^52 + 128 nkc.
+// one thread: 4 consecutive m of one row n (56 registers -> 4 resident CTAs per SM: the kernel is bound by the latency of
+// its residue loads, ncu r02: 52 % long_scoreboard at 25 % occupancy with 8 m per thread).  No conversion-pipe
+// instruction in the inner loop: a residue byte u = y + 128 becomes the double 2^52 + u by a byte permute into the low
+// mantissa word, one DADD removes 2^52 + 128 nkc.
 template <bool ONE_CHUNK>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 crt_reconstruct_kernel(const __grid_constant__ CrtReconArgs a, const __grid_constant__ CrtTables T) {
-  const long long cols8 = a.Mp >> 3;
+  const long long cols4 = a.Mp >> 2;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long n = idx / cols8, m8 = (idx - n * cols8) * 8;
-  if (n >= a.rows || m8 >= a.cols) return;
-  double s1r[8], s2r[8], s1i[8], s2i[8];
+  const long long n = idx / cols4, m4 = (idx - n * cols4) * 4;
+  if (n >= a.rows || m4 >= a.cols) return;
+  double s1r[4], s2r[4], s1i[4], s2i[4];
 #pragma unroll
-  for (int j = 0; j < 8; j++) { s1r[j] = s2r[j] = s1i[j] = s2i[j] = 0.0; }
+  for (int j = 0; j < 4; j++) { s1r[j] = s2r[j] = s1i[j] = s2i[j] = 0.0; }
   const long long plane = a.Np * a.Mp;
-  const int8_t* base = a.R + n * a.Mp + m8;
+  const int8_t* base = a.R + n * a.Mp + m4;
   const double bias = 4503599627370496.0 + 128.0 * (double)a.nkc;   // 2^52 + 128 per chunk
-#pragma unroll 4
+#pragma unroll 8
   for (int i = 0; i < T.nmod; i++) {
-    uint32_t ur[8], ui[8];     // byte sums over the K chunks (still == C' + 128 nkc mod m_i)
+    uint32_t ur[4], ui[4];     // byte sums over the K chunks (still == C' + 128 nkc mod m_i)
     if (ONE_CHUNK) {
-      const uint2 wr = __ldg(reinterpret_cast<const uint2*>(base + (long long)(i * 2) * plane));
-      const uint2 wi = __ldg(reinterpret_cast<const uint2*>(base + (long long)(i * 2 + 1) * plane));
+      const uint32_t wr = __ldg(reinterpret_cast<const uint32_t*>(base + (long long)(i * 2) * plane));
+      const uint32_t wi = __ldg(reinterpret_cast<const uint32_t*>(base + (long long)(i * 2 + 1) * plane));
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        ur[j] = __byte_perm(wr.x, 0, 0x4440 + j); ur[4 + j] = __byte_perm(wr.y, 0, 0x4440 + j);
-        ui[j] = __byte_perm(wi.x, 0, 0x4440 + j); ui[4 + j] = __byte_perm(wi.y, 0, 0x4440 + j);
-      }
+      for (int j = 0; j < 4; j++) { ur[j] = __byte_perm(wr, 0, 0x4440 + j); ui[j] = __byte_perm(wi, 0, 0x4440 + j); }
     } else {
 #pragma unroll
-      for (int j = 0; j < 8; j++) { ur[j] = 0; ui[j] = 0; }
+      for (int j = 0; j < 4; j++) { ur[j] = 0; ui[j] = 0; }
       for (int c = 0; c < a.nkc; c++) {
         const int8_t* pr = base + (long long)((i * a.nkc + c) * 2) * plane;
-        const uint2 wr = __ldg(reinterpret_cast<const uint2*>(pr));
-        const uint2 wi = __ldg(reinterpret_cast<const uint2*>(pr + plane));
+        const uint32_t wr = __ldg(reinterpret_cast<const uint32_t*>(pr));
+        const uint32_t wi = __ldg(reinterpret_cast<const uint32_t*>(pr + plane));
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          ur[j] += __byte_perm(wr.x, 0, 0x4440 + j); ur[4 + j] += __byte_perm(wr.y, 0, 0x4440 + j);
-          ui[j] += __byte_perm(wi.x, 0, 0x4440 + j); ui[4 + j] += __byte_perm(wi.y, 0, 0x4440 + j);
-        }
+        for (int j = 0; j < 4; j++) { ur[j] += __byte_perm(wr, 0, 0x4440 + j); ui[j] += __byte_perm(wi, 0, 0x4440 + j); }
       }
     }
     const double r1 = T.rho1[i], r2 = T.rho2[i];
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
+    for (int j = 0; j < 4; j++) {
       // y * rho1 is exact (|y| <= 2^12, rho1 on a 2^-34 grid) and so is the sum over <= 20 moduli (|S1| < 2^17)
       const double dr = __hiloint2double(0x43300000, (int)ur[j]) - bias;
       const double di = __hiloint2double(0x43300000, (int)ui[j]) - bias;
@@ -571,12 +575,12 @@ crt_reconstruct_kernel(const __grid_constant__ CrtReconArgs a, const __grid_cons
     }
   }
   const int en = crt_exp_from_bits(a.max_n[n]);
-  double2* dst = a.C + n * a.ldc + m8;
+  double2* dst = a.C + n * a.ldc + m4;
   const double RMAGIC = 6755399441055744.0;
 #pragma unroll
-  for (int j = 0; j < 8; j++) {
-    if (m8 + j >= a.cols) break;
-    const int em = crt_exp_from_bits(a.max_m[m8 + j]);
+  for (int j = 0; j < 4; j++) {
+    if (m4 + j >= a.cols) break;
+    const int em = crt_exp_from_bits(a.max_m[m4 + j]);
     double2 out;
     if (en == kExpNonFinite || em == kExpNonFinite) {
       out = make_double2(__longlong_as_double(0x7ff8000000000000LL), __longlong_as_double(0x7ff8000000000000LL));
@@ -673,7 +677,7 @@ int launch_k1_crt(tncb_ctx* ctx, const PairPlan& P, const double2* A, const doub
   unsigned long long* max_m = max_n + pn;
 
   static bool attr_done = false;
-  const int smem_gemm = CRT_STAGES * CRT_STAGE_BYTES + 4 * CRT_STG_BYTES + 1024;
+  const int smem_gemm = CRT_STAGES * CRT_STAGE_BYTES + 8 * CRT_STG_BYTES + 1024;
   const int smem_res = RES_ROWS * RES_RS * (int)sizeof(double2);
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(crt_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_gemm);
@@ -749,7 +753,7 @@ int launch_k1_crt(tncb_ctx* ctx, const PairPlan& P, const double2* A, const doub
       CrtReconArgs r;
       r.R = (const int8_t*)pr; r.C = C + n0 * P.M + m0; r.max_n = max_n; r.max_m = max_m;
       r.rows = nrows; r.cols = mcols; r.ldc = P.M; r.Np = Np; r.Mp = Mp; r.nkc = nkc;
-      const long long threads = nrows * (Mp / 8);
+      const long long threads = nrows * (Mp / 4);
       if (nkc == 1) crt_reconstruct_kernel<true><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(r, T);
       else crt_reconstruct_kernel<false><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(r, T);
       ctx->launches += 2;
