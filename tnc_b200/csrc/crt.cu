@@ -164,23 +164,34 @@ __global__ void __launch_bounds__(256)
 crt_rowmax_kernel(const double2* __restrict__ src, const long long* __restrict__ off_row, const long long* __restrict__ off_k,
                   long long rows, long long K, int lk, unsigned long long* __restrict__ rowmax) {
   __shared__ unsigned long long s_max[RES_ROWS_C];
+  __shared__ long long s_offr[RES_ROWS_C], s_offk[RES_K_C];
   const long long row0 = (long long)blockIdx.x * RES_ROWS_C, k0 = (long long)blockIdx.y * RES_K_C;
   const int tid = threadIdx.x;
-  if (tid < RES_ROWS_C) s_max[tid] = 0ull;
+  // the tile's offset tables first (one round trip), then 16 independent element loads per thread (a second one)
+  if (tid < RES_ROWS_C) { s_max[tid] = 0ull; s_offr[tid] = row0 + tid < rows ? __ldg(off_row + row0 + tid) : -1; }
+  else if (tid >= 128) { const int k = tid - 128; s_offk[k] = k0 + k < K ? __ldg(off_k + k0 + k) : -1; }
   __syncthreads();
-  // one 32 x 128 tile per CTA, 16 independent loads per thread; a thread's row changes at most 2^lk times over the
-  // iterations (never for lk = 0), so its running maximum is flushed to shared memory only when the row changes
-  int cur_r = -1;
-  unsigned long long cur_m = 0ull;
-#pragma unroll 4
+  unsigned long long mv[RES_ROWS_C * RES_K_C / 256];
+#pragma unroll
   for (int it = 0; it < RES_ROWS_C * RES_K_C / 256; it++) {
     int r, k;
     crt_tile_coord(it * 256 + tid, lk, r, k);
-    unsigned long long m = 0ull;
-    if (row0 + r < rows && k0 + k < K) {
-      const double2 v = __ldg(src + __ldg(off_row + row0 + r) + __ldg(off_k + k0 + k));
-      m = max((unsigned long long)__double_as_longlong(fabs(v.x)), (unsigned long long)__double_as_longlong(fabs(v.y)));
+    const long long orow = s_offr[r], ok = s_offk[k];
+    mv[it] = 0ull;
+    if (orow >= 0 && ok >= 0) {
+      const double2 v = __ldg(src + orow + ok);
+      mv[it] = max((unsigned long long)__double_as_longlong(fabs(v.x)), (unsigned long long)__double_as_longlong(fabs(v.y)));
     }
+  }
+  // a thread's row changes at most 2^lk times over the iterations (never for lk = 0), so its running maximum is flushed
+  // to shared memory only when the row changes
+  int cur_r = -1;
+  unsigned long long cur_m = 0ull;
+#pragma unroll
+  for (int it = 0; it < RES_ROWS_C * RES_K_C / 256; it++) {
+    int r, k;
+    crt_tile_coord(it * 256 + tid, lk, r, k);
+    unsigned long long m = mv[it];
     // lanes with the same row sit next to each other (2^lk of them): reduce over them, lane 0 of the group keeps the result
     for (int d = 1; d < (1 << lk); d <<= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
     if (r != cur_r) {
@@ -208,27 +219,42 @@ crt_residue_kernel(const double2* __restrict__ src, const long long* __restrict_
   extern __shared__ __align__(16) unsigned char res_smem_raw[];
   double2* tile = reinterpret_cast<double2*>(res_smem_raw);
   __shared__ double s_scale[RES_ROWS];
+  __shared__ long long s_offr[RES_ROWS], s_offk[RES_K];
+  __shared__ double s_inv[CRT_MAX_MOD];      // the moduli tables out of the constant bank: an LDC with a register index
+  __shared__ int s_mod[CRT_MAX_MOD];         // per loop trip was 35 % of this kernel's stall samples (ncu r02)
   const long long row0 = (long long)blockIdx.x * RES_ROWS, k0 = (long long)blockIdx.y * RES_K;
   const int tid = threadIdx.x;
+  const double two_a = scalbn(1.0, bits);
+  if (tid >= 64 && tid < 64 + CRT_MAX_MOD) { s_inv[tid - 64] = T.inv_mod[tid - 64]; s_mod[tid - 64] = T.mod[tid - 64]; }
+  // the tile's offset tables and row scales first (one round trip), then 16 independent element loads per thread
   if (tid < RES_ROWS) {
     const long long r = row0 + tid;
     const int e = r < rows ? crt_exp_from_bits(rowmax[r]) : 0;
     s_scale[tid] = (e == kExpNonFinite) ? 0.0 : scalbn(1.0, -e);   // non-finite rows contribute zeros (outputs are poisoned later)
+    s_offr[tid] = r < rows ? __ldg(off_row + r) : -1;
+  } else if (tid >= 128) {
+    const int k = tid - 128;
+    s_offk[k] = k0 + k < K ? __ldg(off_k + k0 + k) : -1;
   }
   __syncthreads();
-  const double two_a = scalbn(1.0, bits);
-#pragma unroll 4
+  double2 vv[RES_ROWS * RES_K / 256];
+#pragma unroll
   for (int it = 0; it < RES_ROWS * RES_K / 256; it++) {
     int r, k;
     crt_tile_coord(it * 256 + tid, lk, r, k);
-    double2 v = make_double2(0.0, 0.0);
-    if (row0 + r < rows && k0 + k < K) {
-      v = __ldg(src + __ldg(off_row + row0 + r) + __ldg(off_k + k0 + k));
-      const double sc = s_scale[r];
-      v.x = trunc(v.x * sc * two_a);    // (x * 2^-e) is exact, * 2^a is exact, |.| < 2^a <= 2^53
-      v.y = trunc(v.y * sc * two_a);
-      if (sc == 0.0) { v.x = 0.0; v.y = 0.0; }   // (Inf * 0 = NaN)
-    }
+    const long long orow = s_offr[r], ok = s_offk[k];
+    vv[it] = make_double2(0.0, 0.0);
+    if (orow >= 0 && ok >= 0) vv[it] = __ldg(src + orow + ok);
+  }
+#pragma unroll
+  for (int it = 0; it < RES_ROWS * RES_K / 256; it++) {
+    int r, k;
+    crt_tile_coord(it * 256 + tid, lk, r, k);
+    const double sc = s_scale[r];
+    double2 v = vv[it];
+    v.x = trunc(v.x * sc * two_a);    // (x * 2^-e) is exact, * 2^a is exact, |.| < 2^a <= 2^53
+    v.y = trunc(v.y * sc * two_a);
+    if (sc == 0.0) { v.x = 0.0; v.y = 0.0; }   // (Inf * 0 = NaN)
     tile[r * RES_RS + k + (k >> 3)] = v;
   }
   __syncthreads();
@@ -248,10 +274,11 @@ crt_residue_kernel(const double2* __restrict__ src, const long long* __restrict_
       lr[j] = (int)__double2ll_rn(v.x); li[j] = (int)__double2ll_rn(v.y);
     }
     int8_t* dst = planes + (row0 + r) * Kp + k0 + g * 8;
+    const int nmod = T.nmod;
 #pragma unroll 1
-    for (int i = 0; i < T.nmod; i++) {
-      const int m = T.mod[i];
-      const double inv = T.inv_mod[i];
+    for (int i = 0; i < nmod; i++) {
+      const int m = s_mod[i];
+      const double inv = s_inv[i];
       uint32_t wr[2] = {0, 0}, wi[2] = {0, 0};
 #pragma unroll
       for (int j = 0; j < 8; j++) {
@@ -692,8 +719,9 @@ int launch_k1_crt(tncb_ctx* ctx, const PairPlan& P, const double2* A, const doub
     auto p2 = [](long long d) { int b = 0; while ((2LL << b) <= d && b < 5) b++; return b; };
     const long long ks = kl.n ? (k_is_b ? kl.sb[kl.n - 1] : kl.sa[kl.n - 1]) : (1LL << 62);
     const long long fs = fl.n ? fl.sa[fl.n - 1] : (1LL << 62);
-    if (ks <= fs) return kl.n ? p2(kl.dim[kl.n - 1]) : 0;          // k fastest
-    return 5 - (fl.n ? p2(fl.dim[fl.n - 1]) : 5);                   // rows fastest
+    if (ks <= fs) return kl.n ? p2(kl.dim[kl.n - 1]) : 0;          // k fastest: as many k lanes as that leg is long
+    return 0;   // rows fastest: all lanes along rows (the K list's last group need not be this operand's fastest K leg,
+                // so lanes along k could land on far-apart addresses)
   };
   const int lk_b = lane_split(P.k, true, P.n), lk_a = lane_split(P.k, false, P.m);
   ctx->last_int8_ops = 0.0; ctx->last_nmod = nmod;
