@@ -703,7 +703,8 @@ int launch_k1_crt(tncb_ctx* ctx, const PairPlan& P, const double2* A, const doub
   unsigned long long* max_n = (unsigned long long*)pe;
   unsigned long long* max_m = max_n + pn;
 
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {false};          // cudaFuncSetAttribute is per device
+  bool& attr_done = attr_done_dev[ctx->device & 63];
   const int smem_gemm = CRT_STAGES * CRT_STAGE_BYTES + 8 * CRT_STG_BYTES + 1024;
   const int smem_res = RES_ROWS * RES_RS * (int)sizeof(double2);
   if (!attr_done) {

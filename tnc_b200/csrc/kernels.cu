@@ -988,7 +988,8 @@ int launch_permute(tncb_ctx* ctx, const double2* in, double2* out, int rank,
   for (int g = 0; g < n; g++) if (ext[g] == 1) { a.rcount[a.nr] = L.dim[g]; a.rin[a.nr] = L.sa[g]; a.rout[a.nr] = ostr[g]; a.rtile[a.nr] = -1; a.nr++; blocks *= L.dim[g]; }
   if (blocks > 0x7fffffffLL) return fail(TNCB_ERR_UNSUPPORTED, "permute grid too large");
   const int smem = (int)((te + te / 32 + 1) * sizeof(double2));
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {false};          // cudaFuncSetAttribute is per device
+  bool& attr_done = attr_done_dev[ctx->device & 63];
   if (!attr_done) { TNCB_CUDA(cudaFuncSetAttribute(k3_transpose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (K3_TILE + K3_TILE / 32 + 1) * (int)sizeof(double2))); attr_done = true; }
   int rc = ensure_tab(ctx, (size_t)(5 * te));
   if (rc) return rc;

@@ -1,12 +1,14 @@
-// K1' -- the dense contraction on the 5th-gen tensor cores (tcgen05) by exact int8 slicing.
+// K1' (LEGACY engine, round 1; selectable with tncb_ctx_set_tcgen05_engine(ctx, 1) for A/B measurements -- the default
+// engine is the modular / CRT emulation in crt.cu, which needs 16 int8 GEMM sweeps where this one needs 36).
 //
-// tcgen05.mma has no f64 kind, so a complex128 GEMM reaches the tcgen05 pipe only through an
-// error-free transformation (Ozaki scheme): every real operand row is scaled by a power of two
-// and cut into S signed 7-bit digit planes,
+// The dense contraction on the 5th-gen tensor cores (tcgen05) by 7-bit digit slicing (Ozaki scheme I): every real operand
+// row is scaled by a power of two and cut into S signed 7-bit digit planes,
 //     x * 2^-e = sum_{p<S} d_p * 128^-(p+1) + r,   |d_p| <= 127,  |r| < 128^-S,
-// so that  C = sum_{t<S} 128^-(t+2) * sum_{p+q=t} (D^B_p . D^A_q)  with every D.D an *exact* int8
-// GEMM (int32 accumulation in TMEM, K chunked so it cannot overflow) and the recombination in
-// FP64.  The leg permutation of the reference's TTGT is fused into the slicing pass (gather
+// and  C ~= sum_{t<S} 128^-(t+2) * sum_{p+q=t} (D^B_p . D^A_q)  with every D.D an exact int8 GEMM (int32 accumulation in
+// TMEM, K chunked so it cannot overflow) and the recombination in FP64.  NOT exact: the digit products with p + q >= S are
+// dropped, so |C - C_exact|[n,m] <= (S+1) K 2^(-7S) * 4 max|b[n,:]| max|a[m,:]| (S = 8: measured 1e-15..7e-15 of max|C|),
+// rows containing NaN / Inf give unspecified finite values (the CRT engine poisons them with NaN), and there is no tolerance
+// control beyond the digit count.  The leg permutation of the reference's TTGT is fused into the slicing pass (gather
 // through the plan's offset tables), which writes K-major int8 planes that TMA can stream.
 //
 // Complex arithmetic without int negation in the MMA: planes Br, Bi for Bt and nAi(=-Ai), Ar, Ai
@@ -14,7 +16,7 @@
 //     Br x [Ar ; Ai]^T  -> (real | imag) columns,    Bi x [nAi ; Ar]^T -> (real | imag) columns
 // are two N=256 UMMAs into one 256-column accumulator (cols 0..127 real, 128..255 imag).
 //
-// Kernel structure (one CTA per 128x128 complex output tile, 192 threads):
+// Kernel structure (one CTA per 128x128 complex output tile, 192 threads; oz_gemm2_kernel: CTA pairs, cta_group::2):
 //   warp 0  TMA producer (cp.async.bulk.tensor, SWIZZLE_128B, mbarrier complete_tx)
 //   warp 1  TMEM allocator + single-thread tcgen05.mma.kind::i8 issuer
 //   warps 2-5 epilogue: tcgen05.ld -> int32 -> FP64 * 2^(e_n + e_m - 7(t+2)) -> C (+=)
