@@ -199,6 +199,33 @@ def test_nonfinite_rows_poison_their_outputs(tc_ctx):
     assert np.abs(got[~bad] - ref[~bad]).max() <= 1e-12 * np.abs(ref).max()
 
 
+def test_extreme_exponents(tc_ctx):
+    """Rows near the ends of the double range: maxima of 2^-1040 (denormal: the scale exponent is clamped at -1000, the row
+    keeps ABSOLUTE accuracy 2^(-1000-53)), 2^-900, 1 and 2^+900 against columns of 2^-100 .. 2^+20; every finite product is
+    within the bound relative to max|b row| * max(|a row|, 2^-1000)."""
+    import tnc_b200 as tb
+    rng = np.random.default_rng(9)
+    M, N, K = 256, 128, 384
+    a, b = rand_c(rng, (M, K)), rand_c(rng, (K, N))
+    ea = np.zeros(M, dtype=int); ea[:64] = -1040; ea[64:128] = -900; ea[192:] = 900
+    eb = rng.integers(-100, 20, size=N)
+    a2 = np.ldexp(a.real, ea[:, None]) + 1j * np.ldexp(a.imag, ea[:, None])
+    b2 = np.ldexp(b.real, eb[None, :]) + 1j * np.ldexp(b.imag, eb[None, :])
+    tc_ctx.reset_stats()
+    _, got = tb.contract_pair(tc_ctx, [0, 1], a2, [1, 2], b2)
+    assert tc_ctx.engine_counts()["k1_tcgen05"] == 1
+    ref = b2.T.astype(np.clongdouble) @ a2.T.astype(np.clongdouble)
+    assert np.all(np.isfinite(got.real)) and np.all(np.isfinite(got.imag))
+    mxa = np.maximum(np.maximum(np.abs(a2.real), np.abs(a2.imag)).max(axis=1), 2.0 ** -1001)
+    mxb = np.maximum(np.abs(b2.real), np.abs(b2.imag)).max(axis=0)
+    bound = tb.tcgen05_bound(K)["bound"]
+    ratio = np.abs(got - ref) / (mxb[:, None].astype(np.longdouble) * mxa[None, :].astype(np.longdouble))
+    assert float(ratio.max()) <= bound, float(ratio.max())
+    big = np.abs(ref) > 0
+    rel = (np.abs(got - ref)[:, 64:] / np.abs(ref)[:, 64:]).astype(np.float64)      # normal rows: relative accuracy as usual
+    assert np.median(rel) < 1e-14
+
+
 def test_panels_when_the_workspace_is_small(tc_ctx):
     """A tiny workspace budget forces panels over M and N; results must not change."""
     import tnc_b200 as tb

@@ -648,7 +648,11 @@ int tncb_plan_create(tncb_ctx* ctx, const tncb_tn* tn, const tncb_path* path, tn
 int tncb_plan_execute(tncb_ctx* ctx, tncb_plan* plan, const tncb_tn* tn, tncb_tensor** out, int* n_out, uint64_t* out_legs) {
   if (!ctx || !plan || !tn) return tncb::fail(TNCB_ERR_INVALID, "null argument");
   static const bool trace = std::getenv("TNCB_TRACE") != nullptr;   // per-step times come from the pair-by-pair executor
-  if (plan->is_static && !trace && (plan->ctx == nullptr || plan->ctx == ctx)) return tncb::execute_static(ctx, plan, tn, out, n_out, out_legs);
+  if (plan->is_static && !trace && (plan->ctx == nullptr || plan->ctx == ctx)) {
+    int rc = tncb::execute_static(ctx, plan, tn, out, n_out, out_legs);
+    if (rc != TNCB_ERR_OOM || plan->ws) return rc;
+    plan->is_static = false;        // no room for the static workspace (it keeps a whole tree level alive): pair-by-pair executor
+  }
   return tncb::execute(ctx, plan->S, tn, out, n_out, out_legs);
 }
 
@@ -667,8 +671,11 @@ int tncb_plan_stage(tncb_ctx* ctx, tncb_plan* plan, const tncb_tn* tn) {
   if (rc) return rc;
   const size_t bytes = std::max<size_t>(S.leaf_block_elems * sizeof(double2), 16);
   std::vector<std::complex<double>> host(std::max<size_t>(S.leaf_block_elems, 1));
+  if (plan->is_static && (rc = tncb::plan_device_state(ctx, plan))) {
+    if (rc != TNCB_ERR_OOM || plan->ws) return rc;
+    plan->is_static = false;    // the static workspace does not fit: resident leaf block + pair-by-pair executor
+  }
   if (plan->is_static) {      // the leaf block lives inside the plan workspace
-    if ((rc = tncb::plan_device_state(ctx, plan))) return rc;
     TNCB_CUDA(cudaStreamSynchronize(ctx->stream));
     if ((rc = tncb::stage_leaves(S, leaves, (std::complex<double>*)plan->stage))) return rc;
     TNCB_CUDA(cudaMemcpyAsync((char*)plan->ws + plan->leaf_off, plan->stage, bytes, cudaMemcpyHostToDevice, ctx->stream));
