@@ -42,6 +42,9 @@ class Context {
   Context(const Context&) = delete;
   Context& operator=(const Context&) = delete;
   tncb_ctx* get() const { return h_; }
+  // requested normwise tolerance of the tcgen05 engine (0 = full FP64 mantissa), see tncb_ctx_set_tolerance
+  void set_tolerance(double rel) { check(tncb_ctx_set_tolerance(h_, rel)); }
+  void synchronize() { check(tncb_ctx_synchronize(h_)); }
  private:
   tncb_ctx* h_ = nullptr;
 };
@@ -170,5 +173,47 @@ inline Tensor contract_tensor_network(Context& ctx, Tensor tn, const Contraction
   res.tensordata.device->ctx = ctx.get(); res.tensordata.device->t = out;
   return res;
 }
+
+// Compile once / execute many (tncb_plan_*): the same circuit with other payloads (bitstrings, angles) re-uses the
+// schedule, the static memory layout, the batched tiny pairs and (for launch-bound networks) the CUDA graph.
+class NetworkPlan {
+ public:
+  NetworkPlan(Context& ctx, const Tensor& tn, const ContractionPath& path) : ctx_(ctx) {
+    detail::Marshal m;
+    tncb_tn c_tn = m.tn(tn);
+    tncb_path c_path = m.path(path);
+    check(tncb_plan_create(ctx.get(), &c_tn, &c_path, &h_));
+  }
+  ~NetworkPlan() { tncb_plan_destroy(h_); }
+  NetworkPlan(const NetworkPlan&) = delete;
+  NetworkPlan& operator=(const NetworkPlan&) = delete;
+  Tensor execute(const Tensor& tn) {                 // host leaves -> one H2D -> all kernels
+    detail::Marshal m;
+    tncb_tn c_tn = m.tn(tn);
+    tncb_tensor* out = nullptr; int n_out = 0; uint64_t legs[64];
+    check(tncb_plan_execute(ctx_.get(), h_, &c_tn, &out, &n_out, legs));
+    return wrap(out, n_out, legs);
+  }
+  void stage(const Tensor& tn) { detail::Marshal m; tncb_tn c_tn = m.tn(tn); check(tncb_plan_stage(ctx_.get(), h_, &c_tn)); }
+  Tensor run() {                                     // leaves resident on the device: no host data movement
+    tncb_tensor* out = nullptr; int n_out = 0; uint64_t legs[64];
+    check(tncb_plan_run(ctx_.get(), h_, &out, &n_out, legs));
+    return wrap(out, n_out, legs);
+  }
+ private:
+  Tensor wrap(tncb_tensor* out, int n_out, const uint64_t* legs) {
+    Tensor res;
+    if (!out) return res;
+    res.legs.assign(legs, legs + n_out);
+    res.bond_dims.resize(n_out);
+    if (n_out) check(tncb_tensor_dims(out, res.bond_dims.data()));
+    res.tensordata.kind = TensorData::Device;
+    res.tensordata.device = std::make_shared<DeviceData>();
+    res.tensordata.device->ctx = ctx_.get(); res.tensordata.device->t = out;
+    return res;
+  }
+  Context& ctx_;
+  tncb_plan* h_ = nullptr;
+};
 
 }  // namespace tnc

@@ -67,6 +67,28 @@ static void test_nested(Context& ctx) {
   EXPECT(approx(r.elements()[0], {0.70710678118654752440, 0}));
 }
 
+static void test_plan_and_repeated_calls(Context& ctx) {
+  // the same 5-qubit Hadamard amplitude through a NetworkPlan (execute, stage + run) and through repeated direct calls
+  // (second sighting compiles a cached plan): every route gives the identical value
+  std::vector<Tensor> ts;
+  const int qubits = 5;
+  for (int q = 0; q < qubits; q++) ts.push_back(ket0(q));
+  for (int q = 0; q < qubits; q++) ts.push_back(gate({(uint64_t)q, (uint64_t)(qubits + q)}, "h"));
+  for (int q = 0; q < qubits; q++) ts.push_back(ket0(qubits + q));
+  std::vector<std::pair<size_t, size_t>> p;
+  for (size_t i = 1; i < ts.size(); i++) p.push_back({0, i});
+  const Tensor tn = Tensor::new_composite(ts);
+  const ContractionPath path = ContractionPath::simple(p);
+  const Complex64 direct = contract_tensor_network(ctx, tn, path).elements()[0];
+  NetworkPlan plan(ctx, tn, path);
+  EXPECT(plan.execute(tn).elements()[0] == direct);
+  plan.stage(tn);
+  EXPECT(plan.run().elements()[0] == direct);
+  EXPECT(plan.run().elements()[0] == direct);
+  for (int rep = 0; rep < 3; rep++) EXPECT(contract_tensor_network(ctx, tn, path).elements()[0] == direct);
+  ctx.set_tolerance(1e-10); ctx.set_tolerance(0.0);
+}
+
 int main() {
   try {
     Context ctx(0);
@@ -75,8 +97,9 @@ int main() {
     test_hadamards_amplitude(ctx);
     test_panics_become_errors(ctx);
     test_nested(ctx);
+    test_plan_and_repeated_calls(ctx);
   } catch (const Error& e) { std::printf("FAIL uncaught tnc::Error %d: %s\n", e.status, e.what()); return 2; }
   if (failures) { std::printf("%d failure(s)\n", failures); return 1; }
-  std::printf("HOST_API_OK 5 tests\n");
+  std::printf("HOST_API_OK 6 tests\n");
   return 0;
 }
