@@ -93,6 +93,11 @@ int tncb_ctx_set_tolerance(tncb_ctx* ctx, double rel);
  * log2(prod m_i) >= a + b + log2(K) + 3; counts above what 53-bit operands need for the pair's K are clamped to that
  * (more moduli cannot add accuracy).  Measurement / test aid. */
 int tncb_ctx_set_tcgen05_moduli(tncb_ctx* ctx, int n_moduli);
+/* Real int8 GEMMs per modulus behind one complex product: 4 (re = ArBr - AiBi, im = ArBi + AiBr) or 3 (Gauss's form
+ * k1 = Br(Ar+Ai), k2 = Ar(Bi-Br), k3 = -Ai(Br+Bi); re = k1 + k3, im = k1 + k2 -- the sums are taken on residues, i.e.
+ * exactly, so both forms return bit-identical results).  0 (default) = 3 when K >= min_k3 (default 1024), else 4;
+ * min_k3 <= 0 keeps the current threshold. */
+int tncb_ctx_set_tcgen05_products(tncb_ctx* ctx, int products, long long min_k3);
 /* What K1' would do for contraction length k (no GPU): modulus count, operand bits and the guaranteed factor
  * `bound` with |C - C_exact|[n,m] <= bound * max|b[n,:]| * max|a[m,:]|. */
 int tncb_tcgen05_bound(uint64_t k, double rel, int n_moduli_force, int* n_moduli, int* bits_a, int* bits_b, double* bound);
@@ -109,6 +114,8 @@ int tncb_ctx_set_tcgen05_threshold(tncb_ctx* ctx, long long min_tiles, long long
 int tncb_ctx_engine_counts(tncb_ctx* ctx, uint64_t counts[8]);
 /* int8 operations (2 x MAC) executed by the GEMM kernels of the last K1' pair and its modulus count. */
 int tncb_ctx_last_tcgen05_info(tncb_ctx* ctx, double* int8_ops, int* n_moduli);
+/* ... and whether it used the 3- or the 4-product form. */
+int tncb_ctx_last_tcgen05_products(tncb_ctx* ctx, int* products);
 /* Measurement aid: bracket the dominant GEMM kernel of every large pair (k1_kernel / oz_gemm_kernel)
  * with CUDA events on the ctx stream; tncb_ctx_last_gemm_ms synchronises and returns the last one. */
 int tncb_ctx_time_gemm(tncb_ctx* ctx, int enable);
@@ -282,6 +289,26 @@ int tncb_comm_destroy(tncb_ctx* ctx);
 int tncb_fanin_mapping(size_t n_partitions, const uint64_t* partition_index,
                        size_t n_pairs, const uint64_t* toplevel_pairs, int world_size,
                        int* rank_of_partition);
+
+/* ---- planning aids (host only, no GPU work) ---------------------------------------------------------------
+ * Subtree reconfiguration of a contraction tree -- what the reference gets from cotengra via rustengra
+ * (tnc/src/contractionpath/paths/tree_reconfiguration.rs:54-58).  Legs are relabelled by the caller to bit positions
+ * 0 .. 64*n_words-1; leaf_legs holds n_leaves bitsets of n_words words; leg_log2[l] = log2(dim of leg l); a leg joins at
+ * most two leaves (the reference's tensor model).  ssa_pairs (n_leaves-1 pairs, SSA ids) is refined in place:
+ * pieces of the tree with at most subtree_size (2..15) frontier nodes are re-ordered optimally (subset DP) while that lowers
+ *   sum over pair steps of  prod dims(legs(a) | legs(b)) + size_weight * prod dims(legs(a) ^ legs(b)),
+ * for at most max_sweeps sweeps.  With time_model != NULL (5 doubles: int8-engine flop/s, its K half-rate constant, DMMA
+ * flop/s, HBM byte/s, seconds per launch -- contraction_cost.GPU_RATES) the objective is the modelled device time
+ *   sum over pair steps of  max(8 mnk / rate(m, n, k), 16 (mk + nk + mn) / hbm) + launch
+ * instead.  flops = sum of prod dims(legs(a) | legs(b)), max_size = the largest tensor, objective = the minimised sum. */
+int tncb_path_reconfigure(int n_leaves, int n_words, const uint64_t* leaf_legs, const double* leg_log2, int32_t* ssa_pairs,
+                          int subtree_size, int max_sweeps, double size_weight, const double* time_model, uint64_t seed,
+                          double* flops, double* max_size, double* objective);
+/* Slicing scores of a tree, per leg l (arrays of 64*n_words): cost_without[l] = the objective of ONE slice once l is fixed,
+ * size_without[l] = the largest tensor then; cost / max_size = the unsliced tree's. */
+int tncb_path_leg_scores(int n_leaves, int n_words, const uint64_t* leaf_legs, const double* leg_log2, const int32_t* ssa_pairs,
+                         double size_weight, const double* time_model,
+                         double* cost_without, double* size_without, double* cost, double* max_size);
 
 #ifdef __cplusplus
 }

@@ -14,12 +14,15 @@ def rand_c(rng, shape, scale=1.0):
     return (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)) * scale
 
 
-@pytest.fixture()
-def tc_ctx(built_lib):
+@pytest.fixture(params=[4, 3], ids=["4prod", "3prod"])
+def tc_ctx(built_lib, request):
+    """Every test below runs with the 4-product and with the 3-product (Gauss) form of the complex int8 GEMM."""
     import tnc_b200 as tb
     c = tb.Context(0)
     c.set_tcgen05_slices(8)
     c.set_tcgen05_threshold(1, 128)     # route every pair with M, N >= 128 and K >= 128 to the tcgen05 engine
+    c.set_tcgen05_products(request.param)
+    c.products = request.param
     yield c
     c.close()
 
@@ -62,6 +65,7 @@ def test_engine_is_really_tcgen05(tc_ctx):
     tb.contract_pair_into(tc_ctx, [0, 1], a, [1, 2], b, c)
     assert tc_ctx.stats()["kernel_launches"] == 6
     assert tc_ctx.engine_counts()["k1_tcgen05"] == 1 and tc_ctx.last_tcgen05_info()["n_moduli"] == tb.tcgen05_bound(256)["n_moduli"] == 15
+    assert tc_ctx.last_tcgen05_info()["products"] == tc_ctx.products
     tc_ctx.set_tcgen05_engine(1)                               # legacy digit slicing: 2 exponent + 2 slicing + 1 GEMM
     tc_ctx.reset_stats()
     tb.contract_pair_into(tc_ctx, [0, 1], a, [1, 2], b, c)
@@ -74,6 +78,32 @@ def test_engine_is_really_tcgen05(tc_ctx):
     ec = tc_ctx.engine_counts()
     assert ec["k1_tcgen05"] == 0 and ec["k1_dmma"] + ec["k1_dmma_splitk"] == 1
     tc_ctx.set_tcgen05_slices(8)
+
+
+def test_three_and_four_products_are_bit_identical(built_lib):
+    """Gauss's three-product form takes its sums on residues (exact), so it must reproduce the four-product bits;
+    the default picks it from K >= 1024 (tncb_ctx_set_tcgen05_products)."""
+    import tnc_b200 as tb
+    ctx = tb.Context(0)
+    ctx.set_tcgen05_threshold(1, 128)
+    rng = np.random.default_rng(11)
+    try:
+        for (M, N, K) in [(256, 512, 1024), (384, 136, 2048), (130, 300, 640), (1024, 256, 128 * 33)]:
+            a, b = rand_c(rng, (K, M)), rand_c(rng, (N, K))
+            a *= np.exp(rng.uniform(-30, 30, size=(1, M))); b *= np.exp(rng.uniform(-30, 30, size=(N, 1)))
+            out = {}
+            for pr in (4, 3, 0):
+                ctx.set_tcgen05_products(pr)
+                ctx.reset_stats()
+                _, out[pr] = tb.contract_pair(ctx, [0, 1], a, [2, 0], b)
+                assert ctx.engine_counts()["k1_tcgen05"] == 1
+                assert ctx.last_tcgen05_info()["products"] == (pr if pr else (3 if K >= 1024 else 4))
+            assert np.array_equal(out[3].view(np.float64), out[4].view(np.float64))
+            assert np.array_equal(out[0].view(np.float64), out[4].view(np.float64))
+            ref = b @ a
+            assert np.abs(out[3] - ref).max() <= 1e-12 * np.abs(ref).max()
+    finally:
+        ctx.close()
 
 
 def test_tcgen05_square(tc_ctx):

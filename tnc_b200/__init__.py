@@ -56,6 +56,10 @@ class Context:
     def set_tcgen05_moduli(self, n: int) -> None:
         check(self._l.tncb_ctx_set_tcgen05_moduli(self.handle, int(n)))
 
+    def set_tcgen05_products(self, products: int = 0, min_k3: int = 0) -> None:
+        """3 / 4 real int8 products per complex product (0 = by K), see tncb.h; both forms give identical bits."""
+        check(self._l.tncb_ctx_set_tcgen05_products(self.handle, int(products), int(min_k3)))
+
     def set_tcgen05_workspace(self, nbytes: int) -> None:
         check(self._l.tncb_ctx_set_tcgen05_workspace(self.handle, int(nbytes)))
 
@@ -68,7 +72,9 @@ class Context:
     def last_tcgen05_info(self) -> dict:
         ops, n = C.c_double(), C.c_int()
         check(self._l.tncb_ctx_last_tcgen05_info(self.handle, C.byref(ops), C.byref(n)))
-        return {"int8_ops": ops.value, "n_moduli": n.value}
+        pr = C.c_int()
+        check(self._l.tncb_ctx_last_tcgen05_products(self.handle, C.byref(pr)))
+        return {"int8_ops": ops.value, "n_moduli": n.value, "products": pr.value}
 
     def set_tcgen05_threshold(self, min_tiles: int, min_k: int) -> None:
         check(self._l.tncb_ctx_set_tcgen05_threshold(self.handle, int(min_tiles), int(min_k)))

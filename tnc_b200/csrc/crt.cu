@@ -48,8 +48,13 @@ static const int kModuli[CRT_MAX_MOD] = {256, 253, 251, 249, 247, 245, 241, 239,
 constexpr int CRT_BT = 128;        // tile rows per CTA (n) = tile cols (m)
 constexpr int CRT_BKB = 128;       // K bytes per stage row (one 128-byte swizzle row)
 constexpr int CRT_TILE = CRT_BT * CRT_BKB;      // 16 KB
-constexpr int CRT_STAGES = 3;
-constexpr int CRT_STAGE_BYTES = 4 * CRT_TILE;   // Br, Bi, X (Ar | Ai), Y (-Ai | Ar)
+// shared-memory ring of the GEMM kernel: 192 KB either way
+template <bool KARA> struct CrtRing {
+  static constexpr int TILES = KARA ? 2 : 4;            // four products: Br, Bi, X (Ar | Ai), Y (-Ai | Ar); three: B_p, A_p
+  static constexpr int STAGE_BYTES = TILES * CRT_TILE;
+  static constexpr int STAGES = KARA ? 6 : 3;
+};
+constexpr int CRT_RING_BYTES = 3 * 4 * CRT_TILE;
 constexpr int CRT_THREADS = 320;                // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
 constexpr int CRT_STG_ROW = CRT_BT;              // row of the epilogue staging tile (bytes; 16-byte chunks XOR-swizzled by row)
 constexpr int CRT_STG_BYTES = 32 * CRT_STG_ROW;  // per epilogue warp: 32 rows x 128 residue bytes of one component
@@ -208,10 +213,19 @@ crt_rowmax_kernel(const double2* __restrict__ src, const long long* __restrict__
 // Tile of 32 rows x 128 k: load (coalesced along whichever index is contiguous in the source), scale +
 // truncate to integer-valued doubles in shared memory, then every thread reduces 2 x 8 consecutive k of one row
 // modulo every m_i and writes 8 bytes per plane and pass.
-// planes: [((mod * COMPS + comp) * rowsP + row) * Kp + k];  COMPS == 2: (re, im) -- Bt side,
-// COMPS == 3: (-im, re, im) -- At side.
+// planes: [((mod * NPL + plane) * rowsP + row) * Kp + k];
+//   four-product form:  COMPS == 2 (Bt side): NPL = 2 planes (re, im);  COMPS == 3 (At side): NPL = 3 planes (-im, re, im)
+//   three-product form (KARA, see crt_gemm_kernel): NPL = 3 on both sides, plane p of Bt meets plane p of At:
+//       Bt: (re, im - re, re + im)     At: (re + im, re, -im)
+//   The sums of two residues are brought back into a byte ([-128, 127], still the same class mod m_i) by crt_fix_byte.
+__device__ __forceinline__ int crt_fix_byte(int s, int m) {
+  // |s| <= 256: s > 127 -> s - m in [-125, 83], s < -128 -> s + m in [-83, 124] (173 <= m <= 256; for m = 256 the byte is unchanged)
+  s -= m & ((127 - s) >> 31);
+  s += m & ((s + 128) >> 31);
+  return s;
+}
 constexpr int RES_ROWS = RES_ROWS_C, RES_K = RES_K_C, RES_RS = RES_K + RES_K / 8 + 1;   // padded row stride (elements)
-template <int COMPS>
+template <int COMPS, bool KARA>
 __global__ void __launch_bounds__(256, 3)
 crt_residue_kernel(const double2* __restrict__ src, const long long* __restrict__ off_row, const long long* __restrict__ off_k,
                    long long rows, long long K, long long rowsP, long long Kp, const unsigned long long* __restrict__ rowmax, int bits, int lk,
@@ -279,7 +293,7 @@ crt_residue_kernel(const double2* __restrict__ src, const long long* __restrict_
     for (int i = 0; i < nmod; i++) {
       const int m = s_mod[i];
       const double inv = s_inv[i];
-      uint32_t wr[2] = {0, 0}, wi[2] = {0, 0};
+      uint32_t wr[2] = {0, 0}, wi[2] = {0, 0}, ws[2] = {0, 0};
 #pragma unroll
       for (int j = 0; j < 8; j++) {
         // q = rint(x / m): ONE rounding (the product is exact inside the FMA, the sum has ulp 1); its low 32 bits are
@@ -291,10 +305,24 @@ crt_residue_kernel(const double2* __restrict__ src, const long long* __restrict_
         const int rr = lr[j] - qr * m, ri = li[j] - qi * m;
         constexpr uint32_t sel[4] = {0x3214u, 0x3240u, 0x3410u, 0x4210u};   // low byte of the 2nd operand into byte j & 3
         wr[j >> 2] = __byte_perm(wr[j >> 2], (uint32_t)rr, sel[j & 3]);
-        wi[j >> 2] = __byte_perm(wi[j >> 2], (uint32_t)ri, sel[j & 3]);
+        if (KARA && COMPS == 2) {      // Bt: (re, im - re, re + im)
+          wi[j >> 2] = __byte_perm(wi[j >> 2], (uint32_t)crt_fix_byte(ri - rr, m), sel[j & 3]);
+          ws[j >> 2] = __byte_perm(ws[j >> 2], (uint32_t)crt_fix_byte(rr + ri, m), sel[j & 3]);
+        } else {
+          wi[j >> 2] = __byte_perm(wi[j >> 2], (uint32_t)ri, sel[j & 3]);
+          if (KARA) ws[j >> 2] = __byte_perm(ws[j >> 2], (uint32_t)crt_fix_byte(rr + ri, m), sel[j & 3]);
+        }
       }
-      int8_t* d = dst + (long long)i * COMPS * plane_stride;
-      if (COMPS == 2) {
+      int8_t* d = dst + (long long)i * (KARA ? 3 : COMPS) * plane_stride;
+      if (KARA && COMPS == 2) {
+        *reinterpret_cast<uint2*>(d) = make_uint2(wr[0], wr[1]);
+        *reinterpret_cast<uint2*>(d + plane_stride) = make_uint2(wi[0], wi[1]);
+        *reinterpret_cast<uint2*>(d + 2 * plane_stride) = make_uint2(ws[0], ws[1]);
+      } else if (KARA) {               // At: (re + im, re, -im)
+        *reinterpret_cast<uint2*>(d) = make_uint2(ws[0], ws[1]);
+        *reinterpret_cast<uint2*>(d + plane_stride) = make_uint2(wr[0], wr[1]);
+        *reinterpret_cast<uint2*>(d + 2 * plane_stride) = make_uint2(__vneg4(wi[0]), __vneg4(wi[1]));
+      } else if (COMPS == 2) {
         *reinterpret_cast<uint2*>(d) = make_uint2(wr[0], wr[1]);
         *reinterpret_cast<uint2*>(d + plane_stride) = make_uint2(wi[0], wi[1]);
       } else {
@@ -370,9 +398,10 @@ __device__ __forceinline__ void c_tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 
 struct CrtGemmArgs {
-  int8_t* R;          // residues + 128 as bytes: [((mod * nkc + kc) * 2 + comp) * Np + n] * Mp + m
-  int Np, Mp;         // padded plane rows of this panel (Np % 256 == 0, Mp % 128 == 0)
-  int pairs_n, tiles_m;
+  int8_t* R;          // residues + 128 as bytes: [((mod * nkc + kc) * NPL + plane) * Np + n] * Mp + m
+                      //   four products: NPL = 2 (re, im);  three products: NPL = 3 (k1, k2, k3; re = k1 + k3, im = k1 + k2)
+  int Np, Mp;         // padded plane rows of this panel (Np % 256 == 0, Mp % tile_m == 0)
+  int pairs_n, tiles_m, tile_m;   // tile_m: 128 (four products: 128 re + 128 im columns) or 256 (three products)
   int nmod, nkc, kb_per_chunk, num_kb;
   int total_items;
   int group;          // n-pairs per raster band
@@ -380,12 +409,15 @@ struct CrtGemmArgs {
   int magic[CRT_MAX_MOD];
 };
 
-struct CrtItem { int mod_i, kc, n0, m0; };
+struct CrtItem { int mod_i, prod, kc, n0, m0; };
+template <bool KARA>
 __device__ __forceinline__ CrtItem crt_decode(const CrtGemmArgs& p, int item) {
   const int tiles = p.pairs_n * p.tiles_m;
   const int mk = item / tiles, t = item - mk * tiles;
   CrtItem it;
-  it.mod_i = mk / p.nkc; it.kc = mk - it.mod_i * p.nkc;
+  const int mp = mk / p.nkc;            // (modulus, product) major, K chunk minor
+  it.kc = mk - mp * p.nkc;
+  it.mod_i = KARA ? mp / 3 : mp; it.prod = KARA ? mp - it.mod_i * 3 : 0;
   // grouped raster: bands of `group` n-pairs x all m-tiles; concurrently running pairs (consecutive items)
   // share `group` Bt row bands and ~(#pairs / group) At tiles
   const int per_band = p.group * p.tiles_m;
@@ -393,13 +425,15 @@ __device__ __forceinline__ CrtItem crt_decode(const CrtGemmArgs& p, int item) {
   const int gsize = min(p.group, p.pairs_n - first);
   const int r = t - band * per_band;
   it.n0 = (first + r % gsize) * (2 * CRT_BT);
-  it.m0 = (r / gsize) * CRT_BT;
+  it.m0 = (r / gsize) * p.tile_m;
   return it;
 }
 
+template <bool KARA>
 __global__ void __launch_bounds__(CRT_THREADS, 1)
 crt_gemm_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapA,
                 const __grid_constant__ CrtGemmArgs p) {
+  constexpr int CRT_STAGES = CrtRing<KARA>::STAGES, CRT_STAGE_BYTES = CrtRing<KARA>::STAGE_BYTES;
   extern __shared__ __align__(1024) uint8_t crt_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(crt_smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t full_bar[CRT_STAGES], empty_bar[CRT_STAGES], tfull_bar[2], tempty_bar[2];
@@ -429,16 +463,22 @@ crt_gemm_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant_
     // ================= TMA producer (both CTAs) =================
     int it = 0;
     for (int item = cluster_id; item < p.total_items; item += n_clusters) {
-      const CrtItem w = crt_decode(p, item);
+      const CrtItem w = crt_decode<KARA>(p, item);
       const int kb0 = w.kc * p.kb_per_chunk, kb1 = min(p.num_kb, kb0 + p.kb_per_chunk);
-      const int rowB = (w.mod_i * 2) * p.Np + w.n0 + (int)crank * CRT_BT;   // own 128 of the pair's 256 Bt rows
-      const int rowA = (w.mod_i * 3) * p.Mp + w.m0;
+      // own 128 of the pair's 256 Bt rows; three products: plane `prod` of both operands, own 128 of the 256 At rows
+      const int rowB = (KARA ? w.mod_i * 3 + w.prod : w.mod_i * 2) * p.Np + w.n0 + (int)crank * CRT_BT;
+      const int rowA = (KARA ? (w.mod_i * 3 + w.prod) * p.Mp + w.m0 + (int)crank * CRT_BT : (w.mod_i * 3) * p.Mp + w.m0);
       for (int kb = kb0; kb < kb1; kb++, it++) {
         const int s = it % CRT_STAGES;
         if (it >= CRT_STAGES) c_mbar_wait(&empty_bar[s], ((it / CRT_STAGES) - 1) & 1);
         uint8_t* st = smem + s * CRT_STAGE_BYTES;
         if (leader) c_mbar_expect_tx(&full_bar[s], 2 * CRT_STAGE_BYTES);   // bytes of both CTAs land on the leader's barrier
         const int kx = kb * CRT_BKB;
+        if (KARA) {
+          c_tma_2d_2sm(&mapB, &full_bar[s], st + 0 * CRT_TILE, kx, rowB);           // B_p
+          c_tma_2d_2sm(&mapA, &full_bar[s], st + 1 * CRT_TILE, kx, rowA);           // A_p (N rows 128 crank ...)
+          continue;
+        }
         c_tma_2d_2sm(&mapB, &full_bar[s], st + 0 * CRT_TILE, kx, rowB);             // Br
         c_tma_2d_2sm(&mapB, &full_bar[s], st + 1 * CRT_TILE, kx, rowB + p.Np);      // Bi
         if (leader) {
@@ -456,7 +496,7 @@ crt_gemm_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant_
     const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
     int it = 0, f = 0;
     for (int item = cluster_id; item < p.total_items; item += n_clusters, f++) {
-      const CrtItem w = crt_decode(p, item);
+      const CrtItem w = crt_decode<KARA>(p, item);
       const int kb0 = w.kc * p.kb_per_chunk, kb1 = min(p.num_kb, kb0 + p.kb_per_chunk);
       const int buf = f & 1;
       if (f >= 2) { c_mbar_wait(&tempty_bar[buf], ((f >> 1) - 1) & 1); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -467,13 +507,22 @@ crt_gemm_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant_
         c_mbar_wait(&full_bar[s], (it / CRT_STAGES) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint8_t* st = smem + s * CRT_STAGE_BYTES;
-        const uint64_t d_br = c_desc(st), d_bi = c_desc(st + CRT_TILE), d_x = c_desc(st + 2 * CRT_TILE), d_y = c_desc(st + 3 * CRT_TILE);
+        if (KARA) {
+          const uint64_t d_b = c_desc(st), d_a = c_desc(st + CRT_TILE);
 #pragma unroll
-        for (int k = 0; k < CRT_BKB / 32; k++) {
-          const uint64_t ko = (uint64_t)(k * 32 >> 4);
-          c_umma_i8_2sm(acc, d_br + ko, d_x + ko, idesc, first ? 0u : 1u);   // Br x [Ar ; Ai]
-          first = false;
-          c_umma_i8_2sm(acc, d_bi + ko, d_y + ko, idesc, 1u);               // Bi x [-Ai ; Ar]
+          for (int k = 0; k < CRT_BKB / 32; k++) {
+            c_umma_i8_2sm(acc, d_b + (uint64_t)(k * 32 >> 4), d_a + (uint64_t)(k * 32 >> 4), idesc, first ? 0u : 1u);   // B_p x A_p (256 At rows)
+            first = false;
+          }
+        } else {
+          const uint64_t d_br = c_desc(st), d_bi = c_desc(st + CRT_TILE), d_x = c_desc(st + 2 * CRT_TILE), d_y = c_desc(st + 3 * CRT_TILE);
+#pragma unroll
+          for (int k = 0; k < CRT_BKB / 32; k++) {
+            const uint64_t ko = (uint64_t)(k * 32 >> 4);
+            c_umma_i8_2sm(acc, d_br + ko, d_x + ko, idesc, first ? 0u : 1u);   // Br x [Ar ; Ai]
+            first = false;
+            c_umma_i8_2sm(acc, d_bi + ko, d_y + ko, idesc, 1u);               // Bi x [-Ai ; Ar]
+          }
         }
         c_commit_2sm(&empty_bar[s]);
       }
@@ -485,14 +534,15 @@ crt_gemm_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant_
     // columns 128-255.  Two warps per scheduler hide each other's dependency stalls and keep all four TMEM read ports busy
     // (ncu r02 with four warps: issue slots 35 % busy, the epilogue -- not the MMA -- paced every item with K <= 1024).
     const int q = warp & 3;              // TMEM lane quarter this warp may read
-    const int comp = (warp - 2) >> 2;    // 0: real, 1: imaginary
+    const int comp = (warp - 2) >> 2;    // 0: real, 1: imaginary (three products: At rows 0-127 / 128-255 of the tile)
     int f = 0;
     for (int item = cluster_id; item < p.total_items; item += n_clusters, f++) {
-      const CrtItem w = crt_decode(p, item);
+      const CrtItem w = crt_decode<KARA>(p, item);
       const int buf = f & 1;
       const int m = p.mod[w.mod_i], magic = p.magic[w.mod_i];
       const long long row0 = (long long)w.n0 + (int)crank * CRT_BT + q * 32;     // first of this warp's 32 rows
-      int8_t* dst = p.R + ((long long)((w.mod_i * p.nkc + w.kc) * 2 + comp) * p.Np + row0) * p.Mp + w.m0;
+      int8_t* dst = KARA ? p.R + ((long long)((w.mod_i * p.nkc + w.kc) * 3 + w.prod) * p.Np + row0) * p.Mp + w.m0 + comp * CRT_BT
+                         : p.R + ((long long)((w.mod_i * p.nkc + w.kc) * 2 + comp) * p.Np + row0) * p.Mp + w.m0;
       c_mbar_wait(&tfull_bar[buf], (f >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + comp * CRT_BT);
@@ -559,7 +609,9 @@ struct CrtReconArgs {
 // its residue loads, ncu r02: 52 % long_scoreboard at 25 % occupancy with 8 m per thread).  No conversion-pipe
 // instruction in the inner loop: a residue byte u = y + 128 becomes the double 2^52 + u by a byte permute into the low
 // mantissa word, one DADD removes 2^52 + 128 nkc.
-template <bool ONE_CHUNK>
+// KARA (three products): the planes hold k1, k2, k3 (+128 each); re = k1 + k3 and im = k1 + k2 are formed here as byte sums
+// (== C' + 256 nkc mod m_i -- the CRT sum is linear, no reduction needed: |y| <= 2^13 keeps S1 exact, 13 + 34 + 4.4 bits).
+template <bool ONE_CHUNK, bool KARA>
 __global__ void __launch_bounds__(256, 4)
 crt_reconstruct_kernel(const __grid_constant__ CrtReconArgs a, const __grid_constant__ CrtTables T) {
   const long long cols4 = a.Mp >> 2;
@@ -571,11 +623,26 @@ crt_reconstruct_kernel(const __grid_constant__ CrtReconArgs a, const __grid_cons
   for (int j = 0; j < 4; j++) { s1r[j] = s2r[j] = s1i[j] = s2i[j] = 0.0; }
   const long long plane = a.Np * a.Mp;
   const int8_t* base = a.R + n * a.Mp + m4;
-  const double bias = 4503599627370496.0 + 128.0 * (double)a.nkc;   // 2^52 + 128 per chunk
+  const double bias = 4503599627370496.0 + (KARA ? 256.0 : 128.0) * (double)a.nkc;   // 2^52 + 128 per chunk (and product)
 #pragma unroll 8
   for (int i = 0; i < T.nmod; i++) {
     uint32_t ur[4], ui[4];     // byte sums over the K chunks (still == C' + 128 nkc mod m_i)
-    if (ONE_CHUNK) {
+    if (KARA) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) { ur[j] = 0; ui[j] = 0; }
+      for (int c = 0; c < (ONE_CHUNK ? 1 : a.nkc); c++) {
+        const int8_t* pk = base + (long long)((i * a.nkc + c) * 3) * plane;
+        const uint32_t w1 = __ldg(reinterpret_cast<const uint32_t*>(pk));
+        const uint32_t w2 = __ldg(reinterpret_cast<const uint32_t*>(pk + plane));
+        const uint32_t w3 = __ldg(reinterpret_cast<const uint32_t*>(pk + 2 * plane));
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const uint32_t k1 = __byte_perm(w1, 0, 0x4440 + j);
+          ur[j] += k1 + __byte_perm(w3, 0, 0x4440 + j);
+          ui[j] += k1 + __byte_perm(w2, 0, 0x4440 + j);
+        }
+      }
+    } else if (ONE_CHUNK) {
       const uint32_t wr = __ldg(reinterpret_cast<const uint32_t*>(base + (long long)(i * 2) * plane));
       const uint32_t wi = __ldg(reinterpret_cast<const uint32_t*>(base + (long long)(i * 2 + 1) * plane));
 #pragma unroll
@@ -594,7 +661,7 @@ crt_reconstruct_kernel(const __grid_constant__ CrtReconArgs a, const __grid_cons
     const double r1 = T.rho1[i], r2 = T.rho2[i];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      // y * rho1 is exact (|y| <= 2^12, rho1 on a 2^-34 grid) and so is the sum over <= 20 moduli (|S1| < 2^17)
+      // y * rho1 is exact (|y| <= 2^13, rho1 on a 2^-34 grid) and so is the sum over <= 20 moduli (|S1| < 2^18)
       const double dr = __hiloint2double(0x43300000, (int)ur[j]) - bias;
       const double di = __hiloint2double(0x43300000, (int)ui[j]) - bias;
       s1r[j] = fma(dr, r1, s1r[j]); s2r[j] = fma(dr, r2, s2r[j]);
@@ -665,12 +732,18 @@ int launch_k1_crt(tncb_ctx* ctx, const PairPlan& P, const double2* A, const doub
   const long long Kp = round_up_ll(P.K, CRT_BKB);
   const int num_kb = (int)(Kp / CRT_BKB);
   const int n_clusters_max = std::max(1, ctx->sm_count / 2);
+  // three real products per complex product (Gauss / Karatsuba; sums of residues are exact mod m_i) instead of four: 25 %
+  // fewer int8 operations for one more operand plane and one more residue plane.  An item then carries half the MMA work
+  // per accumulator, so short K (where the epilogue paces the item) keeps the four-product form.
+  const bool kara = ctx->crt_products == 3 || (ctx->crt_products == 0 && Kp >= ctx->crt_kara_min_k);
+  const int TM = kara ? 2 * CRT_BT : CRT_BT;        // At rows per tile
+  const int NPB = kara ? 3 : 2, NPR = kara ? 3 : 2;  // Bt operand planes, residue planes per modulus
   // K chunks: int32-safe length, and more chunks when there are too few tiles to fill the machine (split-K:
   // the reconstruction adds the chunk residues)
-  const long long tiles_total = round_up_ll(P.N, 2 * CRT_BT) / (2 * CRT_BT) * (round_up_ll(P.M, CRT_BT) / CRT_BT);
+  const long long tiles_total = round_up_ll(P.N, 2 * CRT_BT) / (2 * CRT_BT) * (round_up_ll(P.M, TM) / TM);
   int nkc = (int)((Kp + CRT_KCHUNK_MAX - 1) / CRT_KCHUNK_MAX);
   {
-    const long long items = tiles_total * nmod;
+    const long long items = tiles_total * nmod * (kara ? 3 : 1);
     const long long want = 2LL * n_clusters_max;
     if (items * nkc < want) nkc = (int)std::min<long long>((want + items - 1) / items, std::max(1, num_kb / 8));
     nkc = std::max(1, std::min(nkc, 32));      // exactness of the reconstruction: sum of <= 32 chunk residues
@@ -681,17 +754,17 @@ int launch_k1_crt(tncb_ctx* ctx, const PairPlan& P, const double2* A, const doub
 
   // ---- panels: bound the workspace (planes + residues) ----
   const size_t budget = ctx->crt_ws_bytes;
-  long long pn = round_up_ll(P.N, 2 * CRT_BT), pm = round_up_ll(P.M, CRT_BT);   // panel extents (padded)
+  long long pn = round_up_ll(P.N, 2 * CRT_BT), pm = round_up_ll(P.M, TM);   // panel extents (padded)
   auto ws_bytes = [&](long long n_, long long m_) {
-    return (size_t)nmod * (size_t)Kp * (size_t)(2 * n_ + 3 * m_) + (size_t)nmod * nkc * 2 * (size_t)n_ * (size_t)m_;
+    return (size_t)nmod * (size_t)Kp * (size_t)(NPB * n_ + 3 * m_) + (size_t)nmod * nkc * NPR * (size_t)n_ * (size_t)m_;
   };
-  while (ws_bytes(pn, pm) > budget && (pm > CRT_BT || pn > 2 * CRT_BT)) {
-    if (pm >= pn && pm > CRT_BT) pm = round_up_ll(pm / 2, CRT_BT);
+  while (ws_bytes(pn, pm) > budget && (pm > TM || pn > 2 * CRT_BT)) {
+    if (pm >= pn && pm > TM) pm = round_up_ll(pm / 2, TM);
     else if (pn > 2 * CRT_BT) pn = round_up_ll(pn / 2, 2 * CRT_BT);
-    else pm = round_up_ll(pm / 2, CRT_BT);
+    else pm = round_up_ll(pm / 2, TM);
   }
-  const size_t bytesB = (size_t)nmod * 2 * pn * Kp, bytesA = (size_t)nmod * 3 * pm * Kp;
-  const size_t bytesR = (size_t)nmod * nkc * 2 * pn * pm;
+  const size_t bytesB = (size_t)nmod * NPB * pn * Kp, bytesA = (size_t)nmod * 3 * pm * Kp;
+  const size_t bytesR = (size_t)nmod * nkc * NPR * pn * pm;
   const size_t bytesE = (size_t)(pn + pm) * sizeof(unsigned long long);
   void *pb = nullptr, *pa = nullptr, *pr = nullptr, *pe = nullptr;
   int rc;
@@ -705,12 +778,15 @@ int launch_k1_crt(tncb_ctx* ctx, const PairPlan& P, const double2* A, const doub
 
   static bool attr_done_dev[64] = {false};          // cudaFuncSetAttribute is per device
   bool& attr_done = attr_done_dev[ctx->device & 63];
-  const int smem_gemm = CRT_STAGES * CRT_STAGE_BYTES + 8 * CRT_STG_BYTES + 1024;
+  const int smem_gemm = CRT_RING_BYTES + 8 * CRT_STG_BYTES + 1024;
   const int smem_res = RES_ROWS * RES_RS * (int)sizeof(double2);
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(crt_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_gemm);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(crt_residue_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_res);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(crt_residue_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_res);
+    cudaError_t e = cudaFuncSetAttribute(crt_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_gemm);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(crt_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_gemm);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(crt_residue_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_res);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(crt_residue_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_res);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(crt_residue_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_res);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(crt_residue_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_res);
     if (e != cudaSuccess) { cleanup(); return fail(TNCB_ERR_CUDA, cudaGetErrorString(e)); }
     attr_done = true;
   }
@@ -725,41 +801,43 @@ int launch_k1_crt(tncb_ctx* ctx, const PairPlan& P, const double2* A, const doub
                 // so lanes along k could land on far-apart addresses)
   };
   const int lk_b = lane_split(P.k, true, P.n), lk_a = lane_split(P.k, false, P.m);
-  ctx->last_int8_ops = 0.0; ctx->last_nmod = nmod;
+  ctx->last_int8_ops = 0.0; ctx->last_nmod = nmod; ctx->last_products = kara ? 3 : 4;
   bool timed = false;
 
   for (long long n0 = 0; n0 < P.N; n0 += pn) {
     const long long nrows = std::min(pn, P.N - n0);
     const long long Np = round_up_ll(nrows, 2 * CRT_BT);
     // ---- Bt panel: exponents + residues (padding rows / K tail must be zero residues) ----
-    if (Np != nrows) cudaMemsetAsync(pb, 0, (size_t)nmod * 2 * Np * Kp, st);
+    if (Np != nrows) cudaMemsetAsync(pb, 0, (size_t)nmod * NPB * Np * Kp, st);
     cudaMemsetAsync(max_n, 0, (size_t)nrows * sizeof(unsigned long long), st);
     {
       dim3 g((unsigned)((nrows + RES_ROWS - 1) / RES_ROWS), (unsigned)(Kp / RES_K));
       crt_rowmax_kernel<<<g, 256, 0, st>>>(B, offBn + n0, offBk, nrows, P.K, lk_b, max_n);
-      crt_residue_kernel<2><<<g, 256, smem_res, st>>>(B, offBn + n0, offBk, nrows, P.K, Np, Kp, max_n, bits_b, lk_b, T, (int8_t*)pb);
+      if (kara) crt_residue_kernel<2, true><<<g, 256, smem_res, st>>>(B, offBn + n0, offBk, nrows, P.K, Np, Kp, max_n, bits_b, lk_b, T, (int8_t*)pb);
+      else crt_residue_kernel<2, false><<<g, 256, smem_res, st>>>(B, offBn + n0, offBk, nrows, P.K, Np, Kp, max_n, bits_b, lk_b, T, (int8_t*)pb);
     }
     ctx->launches += 2;
     CUtensorMap mapB;
-    if ((rc = crt_make_map(&mapB, pb, (uint64_t)nmod * 2 * Np, (uint64_t)Kp))) { cleanup(); return rc; }
+    if ((rc = crt_make_map(&mapB, pb, (uint64_t)nmod * NPB * Np, (uint64_t)Kp))) { cleanup(); return rc; }
     for (long long m0 = 0; m0 < P.M; m0 += pm) {
       const long long mcols = std::min(pm, P.M - m0);
-      const long long Mp = round_up_ll(mcols, CRT_BT);
+      const long long Mp = round_up_ll(mcols, TM);
       if (Mp != mcols) cudaMemsetAsync(pa, 0, (size_t)nmod * 3 * Mp * Kp, st);
       cudaMemsetAsync(max_m, 0, (size_t)mcols * sizeof(unsigned long long), st);
       {
         dim3 g((unsigned)((mcols + RES_ROWS - 1) / RES_ROWS), (unsigned)(Kp / RES_K));
         crt_rowmax_kernel<<<g, 256, 0, st>>>(A, offAm + m0, offAk, mcols, P.K, lk_a, max_m);
-        crt_residue_kernel<3><<<g, 256, smem_res, st>>>(A, offAm + m0, offAk, mcols, P.K, Mp, Kp, max_m, bits_a, lk_a, T, (int8_t*)pa);
+        if (kara) crt_residue_kernel<3, true><<<g, 256, smem_res, st>>>(A, offAm + m0, offAk, mcols, P.K, Mp, Kp, max_m, bits_a, lk_a, T, (int8_t*)pa);
+        else crt_residue_kernel<3, false><<<g, 256, smem_res, st>>>(A, offAm + m0, offAk, mcols, P.K, Mp, Kp, max_m, bits_a, lk_a, T, (int8_t*)pa);
       }
       ctx->launches += 2;
       CUtensorMap mapA;
       if ((rc = crt_make_map(&mapA, pa, (uint64_t)nmod * 3 * Mp, (uint64_t)Kp))) { cleanup(); return rc; }
       CrtGemmArgs g;
       g.R = (int8_t*)pr; g.Np = (int)Np; g.Mp = (int)Mp;
-      g.pairs_n = (int)(Np / (2 * CRT_BT)); g.tiles_m = (int)(Mp / CRT_BT);
+      g.pairs_n = (int)(Np / (2 * CRT_BT)); g.tiles_m = (int)(Mp / TM); g.tile_m = TM;
       g.nmod = nmod; g.nkc = nkc; g.kb_per_chunk = kb_per_chunk; g.num_kb = num_kb;
-      const long long items = (long long)g.pairs_n * g.tiles_m * nmod * nkc;
+      const long long items = (long long)g.pairs_n * g.tiles_m * nmod * nkc * (kara ? 3 : 1);
       if (items > 0x7fffffffLL) { cleanup(); return fail(TNCB_ERR_UNSUPPORTED, "too many work items"); }
       g.total_items = (int)items;
       g.group = ctx->crt_group;
@@ -772,10 +850,11 @@ int launch_k1_crt(tncb_ctx* ctx, const PairPlan& P, const double2* A, const doub
       attr[0].id = cudaLaunchAttributeClusterDimension;
       attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr; cfg.numAttrs = 1;
-      const double ops = 2.0 * 4.0 * (double)nmod * (double)Np * (double)Mp * (double)Kp;
+      const double ops = 2.0 * (kara ? 3.0 : 4.0) * (double)nmod * (double)Np * (double)Mp * (double)Kp;
       const bool time_this = ctx->time_gemm == 2 || (ctx->time_gemm == 1 && !timed);
       if (time_this) gemm_timer_begin(ctx);
-      cudaError_t e = cudaLaunchKernelEx(&cfg, crt_gemm_kernel, mapB, mapA, g);
+      cudaError_t e = kara ? cudaLaunchKernelEx(&cfg, crt_gemm_kernel<true>, mapB, mapA, g)
+                           : cudaLaunchKernelEx(&cfg, crt_gemm_kernel<false>, mapB, mapA, g);
       if (time_this) { gemm_timer_end(ctx, ops); timed = true; }
       if (e != cudaSuccess) { cleanup(); return fail(TNCB_ERR_CUDA, std::string("crt_gemm_kernel launch: ") + cudaGetErrorString(e)); }
       ctx->last_int8_ops += ops;
@@ -783,8 +862,14 @@ int launch_k1_crt(tncb_ctx* ctx, const PairPlan& P, const double2* A, const doub
       r.R = (const int8_t*)pr; r.C = C + n0 * P.M + m0; r.max_n = max_n; r.max_m = max_m;
       r.rows = nrows; r.cols = mcols; r.ldc = P.M; r.Np = Np; r.Mp = Mp; r.nkc = nkc;
       const long long threads = nrows * (Mp / 4);
-      if (nkc == 1) crt_reconstruct_kernel<true><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(r, T);
-      else crt_reconstruct_kernel<false><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(r, T);
+      const unsigned rg = (unsigned)((threads + 255) / 256);
+      if (kara) {
+        if (nkc == 1) crt_reconstruct_kernel<true, true><<<rg, 256, 0, st>>>(r, T);
+        else crt_reconstruct_kernel<false, true><<<rg, 256, 0, st>>>(r, T);
+      } else {
+        if (nkc == 1) crt_reconstruct_kernel<true, false><<<rg, 256, 0, st>>>(r, T);
+        else crt_reconstruct_kernel<false, false><<<rg, 256, 0, st>>>(r, T);
+      }
       ctx->launches += 2;
     }
   }

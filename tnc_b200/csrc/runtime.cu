@@ -138,6 +138,8 @@ int tncb_ctx_create(int device, size_t arena_bytes, tncb_ctx** out) {
   if (const char* e = std::getenv("TNCB_OZAKI_SLICES")) ctx->oz_slices = std::max(0, std::min(8, atoi(e)));
   if (const char* e = std::getenv("TNCB_TCGEN05_ENGINE")) ctx->oz_engine = atoi(e) == 1 ? 1 : 0;
   if (const char* e = std::getenv("TNCB_CRT_MODULI")) ctx->crt_nmod_force = std::max(0, std::min(20, atoi(e)));
+  if (const char* e = std::getenv("TNCB_CRT_PRODUCTS")) { const int v = atoi(e); ctx->crt_products = (v == 3 || v == 4) ? v : 0; }
+  if (const char* e = std::getenv("TNCB_CRT_MIN_K3")) ctx->crt_kara_min_k = std::max(1, atoi(e));
   if (const char* e = std::getenv("TNCB_CRT_GROUP")) ctx->crt_group = std::max(1, atoi(e));
   if (const char* e = std::getenv("TNCB_CRT_WS_GB")) ctx->crt_ws_bytes = (size_t)std::max(1, atoi(e)) << 30;
   cudaError_t se = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
@@ -279,6 +281,19 @@ int tncb_ctx_set_tolerance(tncb_ctx* ctx, double rel) {
 int tncb_ctx_set_tcgen05_moduli(tncb_ctx* ctx, int n_moduli) {
   if (!ctx || (n_moduli != 0 && (n_moduli < 2 || n_moduli > 20))) return fail(TNCB_ERR_INVALID, "n_moduli must be 0 (auto) or in [2, 20]");
   ctx->crt_nmod_force = n_moduli;
+  return TNCB_OK;
+}
+
+int tncb_ctx_set_tcgen05_products(tncb_ctx* ctx, int products, long long min_k3) {
+  if (!ctx || (products != 0 && products != 3 && products != 4)) return fail(TNCB_ERR_INVALID, "products must be 0 (auto), 3 or 4");
+  ctx->crt_products = products;
+  if (min_k3 > 0) ctx->crt_kara_min_k = min_k3;
+  return TNCB_OK;
+}
+
+int tncb_ctx_last_tcgen05_products(tncb_ctx* ctx, int* products) {
+  if (!ctx || !products) return fail(TNCB_ERR_INVALID, "null argument");
+  *products = ctx->last_products;
   return TNCB_OK;
 }
 

@@ -45,15 +45,16 @@ for (M, N, K) in shapes:
     out["dmma_ms"] = round(ms, 4); out["dmma_tf"] = round(8.0 * M * N * K / ms * 1e-9, 1)
     ctx.set_tcgen05_slices(8)
     ctx.time_gemm(True)
-    for nm in (0, 14, 12):
-        ctx.set_tcgen05_moduli(nm)
+    for nm, pr in ((0, 4), (0, 3), (14, 0), (12, 0)):
+        ctx.set_tcgen05_moduli(nm); ctx.set_tcgen05_products(pr)
         ms = timed()
-        tag = f"crt{ctx.last_tcgen05_info()['n_moduli']}"
+        info = ctx.last_tcgen05_info()
+        tag = f"crt{info['n_moduli']}" + (f"p{pr}" if pr else "")
         out[tag + "_ms"] = round(ms, 4); out[tag + "_tf"] = round(8.0 * M * N * K / ms * 1e-9, 1)
         out[tag + "_gemm_ms"] = round(ctx.last_gemm_ms(), 4)
         if small:
             out[tag + "_err"] = float(np.abs(c.to_numpy() - ref).max() / np.abs(ref).max())
-    ctx.set_tcgen05_moduli(0)
+    ctx.set_tcgen05_moduli(0); ctx.set_tcgen05_products(0)
     if min(M, N, K) >= 256:
         ctx.set_tcgen05_engine(1)
         ms = timed()
