@@ -508,7 +508,7 @@ def run_ours(args):
                                f"has no int8 entry: against its bf16 burst x 2 = {2.0 * bf16_meas:.0f} the fraction is {ach / (2.0 * bf16_meas):.3f}, against nominal 4500 "
                                f"{ach / INT8_NOMINAL_TOPS:.3f}; ncu on the C2 launch: 96 % of the per-cycle pipe peak at a power-capped 1.50 GHz (profiles/r02_ncu_crt_gemm_summary.txt)",
                 "how": f"CUDA events around every one of the {gt['launches']} launches of the kernel inside the timed region (sum of durations "
-                       f"{gt['ms']:.3f} ms = {gt['ms'] / total_ms:.2f} of it); executed int8 ops = 2 x 4 x moduli x Np x Mp x Kp (padded tiles)",
+                       f"{gt['ms']:.3f} ms = {gt['ms'] / total_ms:.2f} of it); executed int8 ops = 2 x (4, or 3 from K >= 4096) x moduli x Np x Mp x Kp (padded tiles)",
                 "kernel_ms_per_step": gt["ms"] / args.steps, "launches_per_step": gt["launches"] / args.steps,
                 "executed_int8_ops_per_step": gt["int8_ops"] / args.steps,
                 "traffic": traffic, "traffic_note": (f"dram read+write of ONE launch on the C2 pair from profiles/{tfile} (ncu --set full of this kernel; not a "
@@ -547,6 +547,15 @@ def run_ours(args):
             extras["parity_n"] = parity_and_modes(tb, ctx, dist, torch, stream, tn, fpath, net, path, amp, rank, world, local, meta_group, max_over_ranks)
     except Exception as e:  # keep the headline line even if an extra leg fails
         extras["extras_error"] = f"{type(e).__name__}: {e}"
+    if not args.no_config5:
+        try:
+            plan = pplan = step_resident = step_e2e = sp = res = r8 = None      # drop the headline workload's device state first
+            import gc
+            gc.collect()
+            ctx.trim()
+            extras["config5_sycamore53_d12"] = config5_sycamore(tb, ctx, dist, rank, world, max_over_ranks)
+        except Exception as e:
+            extras["config5_error"] = f"{type(e).__name__}: {e}"
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -567,6 +576,53 @@ def run_ours(args):
         dist.destroy_process_group()
     if rank == 0 and world > 1 and not extras.get("parity_n", {}).get("ok", False):
         raise SystemExit("multi-GPU parity check failed: " + json.dumps(extras))
+
+
+CONFIG5_PATH = os.path.join("bench_inputs", "sycamore53_d12.json")
+# amplitude <0^53| C |0^53> of the Sycamore-53 depth-12 circuit (seed 1), measured with two independent paths / slicings on
+# a B200 (profiles/r02_config5_sycamore53_d12.jsonl: they agree to 2e-15); regression reference of the config5 object
+CONFIG5_AMPLITUDE = complex(-6.148484459425177e-09, -5.130555022162778e-09)
+
+
+def config5_sycamore(tb, ctx, dist, rank, world, max_over_ranks, steps=2):
+    """BASELINE config 5: Sycamore-53 depth-12 single amplitude as 2^s slices of one replace-left path (found offline by
+    tools/search_path.py: random-greedy + subtree reconfiguration + slicing under the device-time model), slices round-robin
+    over the ranks, one ncclAllReduce.  Timed: every slice through the compiled plan (leaves resident) + all-reduce + D2H of
+    the amplitude, wall clock between barriers, max over ranks."""
+    from tnc_b200.builders import sycamore_circuit
+    from tnc_b200.contractionpath import ContractionPath
+    from tnc_b200.contractionpath.slicing import SlicedPlan, path_cost
+    d = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), CONFIG5_PATH)))
+    w = d["network"].split()
+    tn5 = sycamore_circuit(int(w[1][:-1]), int(w[3]), np.random.default_rng(int(w[5]))).into_amplitude_network("0" * int(w[1][:-1]))[0]
+    path5 = ContractionPath.simple([tuple(x) for x in d["toplevel"]])
+    legs = d["sliced_legs"]
+    flops_slice, peak, _ = path_cost([(t.legs, t.bond_dims) for t in tn5.tensors], path5, legs)
+    t0 = time.perf_counter()
+    sp = SlicedPlan(tn5, path5, legs, ctx=ctx)
+    setup = time.perf_counter() - t0
+    ts, amp5 = [], None
+    for it in range(1 + steps):
+        if world > 1:
+            dist.barrier()
+        ctx.synchronize()
+        t0 = time.perf_counter()
+        amp5 = complex(sp.run(rank, world).to_numpy())
+        dt = max_over_ranks(time.perf_counter() - t0)
+        if it:
+            ts.append(dt)
+    n_slices = sp.n_slices
+    del sp                      # frees the plan's workspace and staged leaves
+    sec = float(np.median(ts))
+    pairs5 = len(path5.toplevel) * n_slices
+    return {"workload": "Sycamore-53 depth-12 single-amplitude network (sycamore_circuit(53, 12), seed 1, bitstring 0^53): 1053 tensors",
+            "path": f"{CONFIG5_PATH}: {d.get('finder', '')}", "mode": f"{n_slices} slices round-robin over {world} rank(s) + 1 ncclAllReduce",
+            "n_gpus": world, "slices": n_slices, "pairs": pairs5, "flops_8mnk": flops_slice * n_slices, "peak_tensor_GiB": peak * 16 / 2 ** 30,
+            "seconds": sec, "seconds_all": [round(t, 4) for t in ts], "setup_seconds_untimed": setup,
+            "contractions_per_s": pairs5 / sec, "zgemm_tflops": flops_slice * n_slices / sec * 1e-12,
+            "amplitude": [amp5.real, amp5.imag], "rel_diff_vs_committed_amplitude": abs(amp5 - CONFIG5_AMPLITUDE) / abs(CONFIG5_AMPLITUDE),
+            "cpu_baseline": "oracle port, 1 of 64 slices of the same path: 87.3 s on 16 cores -> 5586 s extrapolated (tools/bench_sliced.py --cpu-slices 1, "
+                            "profiles/r02_config5_sycamore53_d12.jsonl)"}
 
 
 def parity_and_modes(tb, ctx, dist, torch, stream, tn, fpath, net, path, amp_fanin, rank, world, local, meta_group, max_over_ranks):
@@ -617,6 +673,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pair", action="store_true", help="skip the pair_c2 object")
     ap.add_argument("--no-extras", action="store_true", help="skip the extra objects")
+    ap.add_argument("--no-config5", action="store_true", help="skip the Sycamore-53 depth-12 object (about 30 s at N = 1)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

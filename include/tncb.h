@@ -66,6 +66,12 @@ int tncb_ctx_synchronize(tncb_ctx* ctx);
 /* The CUDA stream every kernel of this ctx is enqueued on (a cudaStream_t). */
 void* tncb_ctx_stream(tncb_ctx* ctx);
 /* Counters since creation / last reset: kernels launched by this library, arena peak. */
+/* Give device memory back to the driver: synchronises, then cudaFree's every arena slab that holds no live block (the
+ * arena otherwise keeps what it reserved for reuse).  For processes that switch between workloads of very different
+ * footprints (e.g. a flat network, then a sliced one with a 64 GiB workspace).  The internal plan cache of
+ * tncb_contract_tensor_network is dropped as well; plans created with tncb_plan_create keep their workspaces until they
+ * are destroyed. */
+int tncb_ctx_trim(tncb_ctx* ctx, uint64_t* freed_bytes, uint64_t* reserved_bytes);
 int tncb_ctx_stats(tncb_ctx* ctx, uint64_t* kernel_launches, uint64_t* arena_peak_bytes,
                    uint64_t* arena_live_bytes);
 int tncb_ctx_reset_stats(tncb_ctx* ctx);
@@ -93,10 +99,12 @@ int tncb_ctx_set_tolerance(tncb_ctx* ctx, double rel);
  * log2(prod m_i) >= a + b + log2(K) + 3; counts above what 53-bit operands need for the pair's K are clamped to that
  * (more moduli cannot add accuracy).  Measurement / test aid. */
 int tncb_ctx_set_tcgen05_moduli(tncb_ctx* ctx, int n_moduli);
-/* Real int8 GEMMs per modulus behind one complex product: 4 (re = ArBr - AiBi, im = ArBi + AiBr) or 3 (Gauss's form
- * k1 = Br(Ar+Ai), k2 = Ar(Bi-Br), k3 = -Ai(Br+Bi); re = k1 + k3, im = k1 + k2 -- the sums are taken on residues, i.e.
- * exactly, so both forms return bit-identical results).  0 (default) = 3 when K >= min_k3 (default 1024), else 4;
- * min_k3 <= 0 keeps the current threshold. */
+/* Real int8 GEMMs per modulus behind one complex product: 4 (re = ArBr - AiBi, im = ArBi + AiBr) or 3 (Karatsuba:
+ * k1 = ArBr, k2 = AiBi, k3 = (Ar+Ai)(Br+Bi); re = k1 - k2, im = k3 - k1 - k2 -- the operand sums are taken on the residues,
+ * i.e. exactly, so both forms reconstruct the same integers and differ only in the last rounding of the reconstruction).
+ * 25 % fewer int8 operations for one more operand plane per side and one more residue plane, which pays from K ~ 4096
+ * (profiles/r02_engine_sweep.jsonl): 0 (default) = 3 when K >= min_k3 (default 4096), else 4; min_k3 <= 0 keeps the
+ * current threshold. */
 int tncb_ctx_set_tcgen05_products(tncb_ctx* ctx, int products, long long min_k3);
 /* What K1' would do for contraction length k (no GPU): modulus count, operand bits and the guaranteed factor
  * `bound` with |C - C_exact|[n,m] <= bound * max|b[n,:]| * max|a[m,:]|. */
@@ -297,9 +305,10 @@ int tncb_fanin_mapping(size_t n_partitions, const uint64_t* partition_index,
  * most two leaves (the reference's tensor model).  ssa_pairs (n_leaves-1 pairs, SSA ids) is refined in place:
  * pieces of the tree with at most subtree_size (2..15) frontier nodes are re-ordered optimally (subset DP) while that lowers
  *   sum over pair steps of  prod dims(legs(a) | legs(b)) + size_weight * prod dims(legs(a) ^ legs(b)),
- * for at most max_sweeps sweeps.  With time_model != NULL (5 doubles: int8-engine flop/s, its K half-rate constant, DMMA
- * flop/s, HBM byte/s, seconds per launch -- contraction_cost.GPU_RATES) the objective is the modelled device time
- *   sum over pair steps of  max(8 mnk / rate(m, n, k), 16 (mk + nk + mn) / hbm) + launch
+ * for at most max_sweeps sweeps.  With time_model != NULL (8 doubles: int8-engine flop/s, its K half-rate constant, FP64
+ * flop/s, HBM byte/s, seconds per launch, the FP64 kernels' K half-rate constant, the int8 engine's largest K, its operand
+ * conversion bytes per element -- contraction_cost.GPU_RATES) the objective is the modelled device time
+ *   sum over pair steps of  max(8 mnk / rate(m, n, k), 16 (mk + nk + mn) / hbm) + launch       (gpu_time_mnk)
  * instead.  flops = sum of prod dims(legs(a) | legs(b)), max_size = the largest tensor, objective = the minimised sum. */
 int tncb_path_reconfigure(int n_leaves, int n_words, const uint64_t* leaf_legs, const double* leg_log2, int32_t* ssa_pairs,
                           int subtree_size, int max_sweeps, double size_weight, const double* time_model, uint64_t seed,

@@ -198,6 +198,33 @@ def test_sliced_equals_flat(ctx):
     assert np.abs(got.to_numpy() - ref.to_numpy()).max() <= 1e-12
 
 
+def test_reconfigured_and_sliced_paths_give_the_same_amplitude(ctx):
+    """The planning chain of BASELINE config 5 on a network the oracle can check: greedy path, TreeReconfigure path
+    (csrc/reconf.cpp) and slice_and_reconfigure + contract_sliced all return the oracle's amplitude."""
+    from tnc_b200.builders import random_circuit
+    from tnc_b200.contractionpath import ContractionPath, ssa_replace_ordering
+    from tnc_b200.contractionpath.paths import TreeReconfigure, slice_and_reconfigure
+    from tnc_b200.contractionpath.paths.cotengrust import optimize_greedy
+    from tnc_b200.contractionpath.slicing import contract_sliced
+    from tnc_b200.tensornetwork import contract_tensor_network
+    tn = random_circuit(20, 10, 0.5, 0.5, np.random.default_rng(11))
+    p0 = greedy(tn)
+    ref = complex(orc.contract_tensor_network(to_oracle(tn), to_opath(p0)).data)
+    opt = TreeReconfigure(tn, 10)
+    opt.find_path()
+    got = complex(contract_tensor_network(tn, opt.get_best_replace_path(), ctx=ctx).to_numpy())
+    assert abs(got - ref) <= 1e-10 * abs(ref) + 1e-14
+    inputs = [list(t.legs) for t in tn.tensors]
+    size = {l: float(d) for t in tn.tensors for l, d in t.edges()}
+    ssa = optimize_greedy(inputs, [], size)
+    for objective in ("flops", "time"):
+        sliced, new, flops, peak, _ = slice_and_reconfigure(inputs, size, ssa, opt.get_best_size() / 64.0, 10, 4, 0.0, 3, 8, objective)
+        assert 1 <= len(sliced) <= 8
+        rp = ssa_replace_ordering(ContractionPath.simple(new))
+        got = complex(contract_sliced(tn, rp, sliced, ctx=ctx).to_numpy())
+        assert abs(got - ref) <= 1e-10 * abs(ref) + 1e-14
+
+
 @pytest.mark.parametrize("name,qubits,rounds", [("C3", 24, 12), ("C4", 36, 10)])
 def test_baseline_networks_vs_oracle(built_lib, name, qubits, rounds):
     """BASELINE.json configs 3 and 4 as networks (seed 1, greedy Cotengrust path): the amplitude through

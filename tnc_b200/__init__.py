@@ -56,6 +56,12 @@ class Context:
     def set_tcgen05_moduli(self, n: int) -> None:
         check(self._l.tncb_ctx_set_tcgen05_moduli(self.handle, int(n)))
 
+    def trim(self) -> dict:
+        """Give unused arena slabs back to the driver (tncb_ctx_trim)."""
+        f, r = C.c_uint64(), C.c_uint64()
+        check(self._l.tncb_ctx_trim(self.handle, C.byref(f), C.byref(r)))
+        return {"freed_bytes": f.value, "reserved_bytes": r.value}
+
     def set_tcgen05_products(self, products: int = 0, min_k3: int = 0) -> None:
         """3 / 4 real int8 products per complex product (0 = by K), see tncb.h; both forms give identical bits."""
         check(self._l.tncb_ctx_set_tcgen05_products(self.handle, int(products), int(min_k3)))

@@ -68,6 +68,7 @@ SIGNATURES = {
     "tncb_ctx_engine_counts": (C.c_int, [C.c_void_p, u64p]),
     "tncb_ctx_last_tcgen05_info": (C.c_int, [C.c_void_p, f64p, i32p]),
     "tncb_ctx_last_tcgen05_products": (C.c_int, [C.c_void_p, i32p]),
+    "tncb_ctx_trim": (C.c_int, [C.c_void_p, u64p, u64p]),
     "tncb_path_reconfigure": (C.c_int, [C.c_int, C.c_int, u64p, f64p, i32p, C.c_int, C.c_int, C.c_double, f64p, C.c_uint64, f64p, f64p, f64p]),
     "tncb_path_leg_scores": (C.c_int, [C.c_int, C.c_int, u64p, f64p, i32p, C.c_double, f64p, f64p, f64p, f64p, f64p]),
     "tncb_ctx_set_tcgen05_products": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong]),

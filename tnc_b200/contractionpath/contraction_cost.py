@@ -121,23 +121,35 @@ def communication_path_op_costs(inputs: Sequence[Tensor], path, only_count_ops: 
 
 # ---- planning-only device time model (NOT in the reference) -------------------------------------------------------
 # The reference scores partitionings by operation counts (contract_op_cost_tensors); on a B200 the pairs that dominate a
-# partitioned contraction are as often bandwidth-bound (boundary tensors of 2^28 elements) as compute-bound, and the
-# fan-in moves them over NVLink.  `gpu_time_tensors` is a two-roof estimate per pair, measured rates of this repo's
-# kernels (profiles/r02_engine_sweep.jsonl, profiles/r02_trace_part*.txt): K1' 160 K/(K+600) TFLOP/s-equivalent for GEMM-like
-# pairs (48 at K=256, 74 at 512, 124 at 2048, 140 at 4096: the residue / reconstruction passes do not shrink with K),
-# ~25 TFLOP/s DMMA otherwise, ~5 TB/s of HBM traffic, ~5 us per launch.  Used by tools/plan_partitions.py to choose
-# among candidate partitionings.
-GPU_RATES = {"crt_flops": 160e12, "crt_k_half": 600.0, "dmma_flops": 25e12, "hbm_bytes": 5e12, "launch_s": 5e-6, "nvlink_bytes": 6e11, "hop_s": 30e-6}
+# partitioned or sliced contraction are as often bandwidth-bound (tensors of 2^28..2^30 elements meeting tiny ones) as
+# compute-bound, and the fan-in moves them over NVLink.  `gpu_time_tensors` is a two-roof estimate per pair from measured
+# rates of this repo's kernels (profiles/r02_engine_sweep.jsonl, r02_trace_part*.txt, r02_trace_sycamore_d12_slice.txt):
+#   * FP64 kernels (K1 DMMA, K2, K0): 34 TFLOP/s x K/(K+12)  (35 at K = 2^23; 18.5 at K = 16; gate-sized K stay HBM-bound);
+#   * K1' (int8 engine; M, N >= 128, 256 <= K <= 2^20, MNK >= 2^28): 160 K/(K+600) TFLOP/s-equivalent (48 at K=256, 74 at 512,
+#     124 at 2048, 140 at 4096: the residue / reconstruction passes do not shrink with K) plus the operand conversion,
+#     40 bytes of residue planes per operand element (what makes M = N = 128, K = 2^20 cost 3 ms more than its GEMM);
+#   * ~5 TB/s of HBM traffic, ~5 us per launch.
+# Used by tools/plan_partitions.py (partitionings) and csrc/reconf.cpp via tools/search_path.py (trees + slices): the C++
+# Objective::pair restates exactly this function and tests/test_tree_reconfiguration.py pins the two against each other.
+GPU_RATES = {"crt_flops": 160e12, "crt_k_half": 600.0, "dmma_flops": 34e12, "hbm_bytes": 5e12, "launch_s": 5e-6,
+             "dmma_k_half": 12.0, "crt_k_max": 1048576.0, "crt_conv_bytes": 40.0, "nvlink_bytes": 6e11, "hop_s": 30e-6}
+
+
+def gpu_time_mnk(m: float, n: float, k: float) -> float:
+    R = GPU_RATES
+    mnk = m * n * k
+    flops = 8.0 * mnk
+    t_mem = 16.0 * (m * k + n * k + m * n) / R["hbm_bytes"]
+    t = max(flops / (R["dmma_flops"] * k / (k + R["dmma_k_half"])), t_mem)
+    if m >= 128 and n >= 128 and 256 <= k <= R["crt_k_max"] and mnk >= 2.0 ** 28:
+        t_crt = flops / (R["crt_flops"] * k / (k + R["crt_k_half"])) + R["crt_conv_bytes"] * (m * k + n * k) / R["hbm_bytes"]
+        t = min(t, max(t_crt, t_mem))
+    return t + R["launch_s"]
 
 
 def gpu_time_tensors(t1: Tensor, t2: Tensor) -> float:
     k = (t1 & t2).size()
-    m, n = (t1 - t2).size(), (t2 - t1).size()
-    flops = 8.0 * m * n * k
-    crt = m >= 128 and n >= 128 and k >= 256 and m * n * k >= 2.0 ** 28
-    t_math = flops / (GPU_RATES["crt_flops"] * k / (k + GPU_RATES["crt_k_half"]) if crt else GPU_RATES["dmma_flops"])
-    t_mem = 16.0 * (m * k + n * k + m * n) / GPU_RATES["hbm_bytes"]
-    return max(t_math, t_mem) + GPU_RATES["launch_s"]
+    return gpu_time_mnk((t1 - t2).size(), (t2 - t1).size(), k)
 
 
 def gpu_fanin_time_tensors(t1: Tensor, t2: Tensor) -> float:

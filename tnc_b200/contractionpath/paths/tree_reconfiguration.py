@@ -62,7 +62,8 @@ def _time_model(objective: str):
     if objective != "time":
         raise ValueError("objective must be 'flops' or 'time'")
     from ..contraction_cost import GPU_RATES as R
-    return np.array([R["crt_flops"], R["crt_k_half"], R["dmma_flops"], R["hbm_bytes"], R["launch_s"]], dtype=np.float64)
+    return np.array([R["crt_flops"], R["crt_k_half"], R["dmma_flops"], R["hbm_bytes"], R["launch_s"], R["dmma_k_half"], R["crt_k_max"],
+                     R["crt_conv_bytes"]], dtype=np.float64)
 
 
 def reconfigure_ssa_path(inputs: Sequence[Sequence[int]], size_dict: Dict[int, float], ssa_path: Sequence[Tuple[int, int]],

@@ -215,13 +215,13 @@ crt_rowmax_kernel(const double2* __restrict__ src, const long long* __restrict__
 // modulo every m_i and writes 8 bytes per plane and pass.
 // planes: [((mod * NPL + plane) * rowsP + row) * Kp + k];
 //   four-product form:  COMPS == 2 (Bt side): NPL = 2 planes (re, im);  COMPS == 3 (At side): NPL = 3 planes (-im, re, im)
-//   three-product form (KARA, see crt_gemm_kernel): NPL = 3 on both sides, plane p of Bt meets plane p of At:
-//       Bt: (re, im - re, re + im)     At: (re + im, re, -im)
-//   The sums of two residues are brought back into a byte ([-128, 127], still the same class mod m_i) by crt_fix_byte.
+//   three-product form (KARA, see crt_gemm_kernel): NPL = 3 on both sides, (re, im, re + im); plane p of Bt meets plane p
+//   of At (Karatsuba: k1 = Br Ar, k2 = Bi Ai, k3 = (Br + Bi)(Ar + Ai); re = k1 - k2, im = k3 - k1 - k2).
+//   The sum of two residues is brought back into a byte ([-128, 127], still the same class mod m_i) by crt_fix_byte.
 __device__ __forceinline__ int crt_fix_byte(int s, int m) {
   // |s| <= 256: s > 127 -> s - m in [-125, 83], s < -128 -> s + m in [-83, 124] (173 <= m <= 256; for m = 256 the byte is unchanged)
-  s -= m & ((127 - s) >> 31);
-  s += m & ((s + 128) >> 31);
+  if (s > 127) s -= m;
+  else if (s < -128) s += m;
   return s;
 }
 constexpr int RES_ROWS = RES_ROWS_C, RES_K = RES_K_C, RES_RS = RES_K + RES_K / 8 + 1;   // padded row stride (elements)
@@ -305,23 +305,14 @@ crt_residue_kernel(const double2* __restrict__ src, const long long* __restrict_
         const int rr = lr[j] - qr * m, ri = li[j] - qi * m;
         constexpr uint32_t sel[4] = {0x3214u, 0x3240u, 0x3410u, 0x4210u};   // low byte of the 2nd operand into byte j & 3
         wr[j >> 2] = __byte_perm(wr[j >> 2], (uint32_t)rr, sel[j & 3]);
-        if (KARA && COMPS == 2) {      // Bt: (re, im - re, re + im)
-          wi[j >> 2] = __byte_perm(wi[j >> 2], (uint32_t)crt_fix_byte(ri - rr, m), sel[j & 3]);
-          ws[j >> 2] = __byte_perm(ws[j >> 2], (uint32_t)crt_fix_byte(rr + ri, m), sel[j & 3]);
-        } else {
-          wi[j >> 2] = __byte_perm(wi[j >> 2], (uint32_t)ri, sel[j & 3]);
-          if (KARA) ws[j >> 2] = __byte_perm(ws[j >> 2], (uint32_t)crt_fix_byte(rr + ri, m), sel[j & 3]);
-        }
+        wi[j >> 2] = __byte_perm(wi[j >> 2], (uint32_t)ri, sel[j & 3]);
+        if (KARA) ws[j >> 2] = __byte_perm(ws[j >> 2], (uint32_t)crt_fix_byte(rr + ri, m), sel[j & 3]);
       }
       int8_t* d = dst + (long long)i * (KARA ? 3 : COMPS) * plane_stride;
-      if (KARA && COMPS == 2) {
+      if (KARA) {
         *reinterpret_cast<uint2*>(d) = make_uint2(wr[0], wr[1]);
         *reinterpret_cast<uint2*>(d + plane_stride) = make_uint2(wi[0], wi[1]);
         *reinterpret_cast<uint2*>(d + 2 * plane_stride) = make_uint2(ws[0], ws[1]);
-      } else if (KARA) {               // At: (re + im, re, -im)
-        *reinterpret_cast<uint2*>(d) = make_uint2(ws[0], ws[1]);
-        *reinterpret_cast<uint2*>(d + plane_stride) = make_uint2(wr[0], wr[1]);
-        *reinterpret_cast<uint2*>(d + 2 * plane_stride) = make_uint2(__vneg4(wi[0]), __vneg4(wi[1]));
       } else if (COMPS == 2) {
         *reinterpret_cast<uint2*>(d) = make_uint2(wr[0], wr[1]);
         *reinterpret_cast<uint2*>(d + plane_stride) = make_uint2(wi[0], wi[1]);
@@ -405,7 +396,7 @@ struct CrtGemmArgs {
   int nmod, nkc, kb_per_chunk, num_kb;
   int total_items;
   int group;          // n-pairs per raster band
-  int mod[CRT_MAX_MOD];
+  int negmod[CRT_MAX_MOD];   // -m_i (kept as data so that the epilogue's a - q m is ONE multiply-add)
   int magic[CRT_MAX_MOD];
 };
 
@@ -539,7 +530,7 @@ crt_gemm_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant_
     for (int item = cluster_id; item < p.total_items; item += n_clusters, f++) {
       const CrtItem w = crt_decode<KARA>(p, item);
       const int buf = f & 1;
-      const int m = p.mod[w.mod_i], magic = p.magic[w.mod_i];
+      const int negm = p.negmod[w.mod_i], magic = p.magic[w.mod_i];
       const long long row0 = (long long)w.n0 + (int)crank * CRT_BT + q * 32;     // first of this warp's 32 rows
       int8_t* dst = KARA ? p.R + ((long long)((w.mod_i * p.nkc + w.kc) * 3 + w.prod) * p.Np + row0) * p.Mp + w.m0 + comp * CRT_BT
                          : p.R + ((long long)((w.mod_i * p.nkc + w.kc) * 2 + comp) * p.Np + row0) * p.Mp + w.m0;
@@ -564,14 +555,18 @@ crt_gemm_kernel(const __grid_constant__ CUtensorMap mapB, const __grid_constant_
         for (int j = 0; j < 32; j++) {
           const int a = (int)v[j];
           // q = floor(a * magic / 2^32) in [a/m - 1.25, a/m + 0.25] (|a| < 2^31, |magic / 2^32 - 1/m| <= 2^-33), so
-          // z = a - q m + 128 lies in (64, 1.25 m + 128]: one conditional subtraction of m leaves the OFFSET byte
-          // (residue + 128) in [0, 255]
-          int z = a - __mulhi(a, magic) * m + 128;
-          z -= (z >> 8) * m;
+          // t = a - q m lies in [-0.25 m, 1.25 m] = [-64, 320]: one conditional subtraction of m leaves a representative in
+          // [-128, 127]; its low byte, with the top bit flipped (once per packed word), is the OFFSET byte residue + 128.
+          // (-m is passed in, the condition is a predicate: IMAD.HI + IMAD are the only multiplier-pipe instructions --
+          // ncu r02, K = 512: that pipe was 68 % busy and paced the item, see profiles/r02_ncu_crt_gemm_k512.txt)
+          int t = __mulhi(a, magic) * negm + a;
+          if (t > 127) t += negm;
           constexpr uint32_t sel[4] = {0x3214u, 0x3240u, 0x3410u, 0x4210u};
           if ((j & 3) == 0) wds[j >> 2] = 0;
-          wds[j >> 2] = __byte_perm(wds[j >> 2], (uint32_t)z, sel[j & 3]);
+          wds[j >> 2] = __byte_perm(wds[j >> 2], (uint32_t)t, sel[j & 3]);
         }
+#pragma unroll
+        for (int j = 0; j < 8; j++) wds[j] ^= 0x80808080u;
         uint8_t* srow = stg + lane * CRT_STG_ROW;
         *reinterpret_cast<uint4*>(srow + (((2 * ch) ^ (lane & 7)) << 4)) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
         *reinterpret_cast<uint4*>(srow + (((2 * ch + 1) ^ (lane & 7)) << 4)) = make_uint4(wds[4], wds[5], wds[6], wds[7]);
@@ -609,8 +604,8 @@ struct CrtReconArgs {
 // its residue loads, ncu r02: 52 % long_scoreboard at 25 % occupancy with 8 m per thread).  No conversion-pipe
 // instruction in the inner loop: a residue byte u = y + 128 becomes the double 2^52 + u by a byte permute into the low
 // mantissa word, one DADD removes 2^52 + 128 nkc.
-// KARA (three products): the planes hold k1, k2, k3 (+128 each); re = k1 + k3 and im = k1 + k2 are formed here as byte sums
-// (== C' + 256 nkc mod m_i -- the CRT sum is linear, no reduction needed: |y| <= 2^13 keeps S1 exact, 13 + 34 + 4.4 bits).
+// KARA (three products): the planes hold k1, k2, k3 (+128 each); re = k1 - k2 and im = k3 - k1 - k2 are formed here from the
+// bytes (the CRT sum is linear, no reduction mod m_i needed: |y| <= 3 * 128 * 32 < 2^13.6 keeps S1 exact, 13.6 + 34 + 4.4 bits).
 template <bool ONE_CHUNK, bool KARA>
 __global__ void __launch_bounds__(256, 4)
 crt_reconstruct_kernel(const __grid_constant__ CrtReconArgs a, const __grid_constant__ CrtTables T) {
@@ -623,7 +618,10 @@ crt_reconstruct_kernel(const __grid_constant__ CrtReconArgs a, const __grid_cons
   for (int j = 0; j < 4; j++) { s1r[j] = s2r[j] = s1i[j] = s2i[j] = 0.0; }
   const long long plane = a.Np * a.Mp;
   const int8_t* base = a.R + n * a.Mp + m4;
-  const double bias = 4503599627370496.0 + (KARA ? 256.0 : 128.0) * (double)a.nkc;   // 2^52 + 128 per chunk (and product)
+  // a byte is u = y + 128; four products: sum of u over chunks - 128 nkc.  Three: re = (u1 - u2 + 256) - 256 per chunk,
+  // im = (u3 - u1 - u2 + 512) - 384 per chunk (the +256 / +512 keep the running sums non-negative for the conversion below)
+  const double bias = 4503599627370496.0 + (KARA ? 256.0 : 128.0) * (double)a.nkc;   // 2^52 + ...
+  const double bias_i = 4503599627370496.0 + (KARA ? 384.0 : 128.0) * (double)a.nkc;
 #pragma unroll 8
   for (int i = 0; i < T.nmod; i++) {
     uint32_t ur[4], ui[4];     // byte sums over the K chunks (still == C' + 128 nkc mod m_i)
@@ -637,9 +635,9 @@ crt_reconstruct_kernel(const __grid_constant__ CrtReconArgs a, const __grid_cons
         const uint32_t w3 = __ldg(reinterpret_cast<const uint32_t*>(pk + 2 * plane));
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-          const uint32_t k1 = __byte_perm(w1, 0, 0x4440 + j);
-          ur[j] += k1 + __byte_perm(w3, 0, 0x4440 + j);
-          ui[j] += k1 + __byte_perm(w2, 0, 0x4440 + j);
+          const uint32_t k1 = __byte_perm(w1, 0, 0x4440 + j), k2 = __byte_perm(w2, 0, 0x4440 + j);
+          ur[j] += 256u + k1 - k2;
+          ui[j] += 512u + __byte_perm(w3, 0, 0x4440 + j) - k1 - k2;
         }
       }
     } else if (ONE_CHUNK) {
@@ -663,7 +661,7 @@ crt_reconstruct_kernel(const __grid_constant__ CrtReconArgs a, const __grid_cons
     for (int j = 0; j < 4; j++) {
       // y * rho1 is exact (|y| <= 2^13, rho1 on a 2^-34 grid) and so is the sum over <= 20 moduli (|S1| < 2^18)
       const double dr = __hiloint2double(0x43300000, (int)ur[j]) - bias;
-      const double di = __hiloint2double(0x43300000, (int)ui[j]) - bias;
+      const double di = __hiloint2double(0x43300000, (int)ui[j]) - bias_i;
       s1r[j] = fma(dr, r1, s1r[j]); s2r[j] = fma(dr, r2, s2r[j]);
       s1i[j] = fma(di, r1, s1i[j]); s2i[j] = fma(di, r2, s2i[j]);
     }
@@ -732,9 +730,9 @@ int launch_k1_crt(tncb_ctx* ctx, const PairPlan& P, const double2* A, const doub
   const long long Kp = round_up_ll(P.K, CRT_BKB);
   const int num_kb = (int)(Kp / CRT_BKB);
   const int n_clusters_max = std::max(1, ctx->sm_count / 2);
-  // three real products per complex product (Gauss / Karatsuba; sums of residues are exact mod m_i) instead of four: 25 %
-  // fewer int8 operations for one more operand plane and one more residue plane.  An item then carries half the MMA work
-  // per accumulator, so short K (where the epilogue paces the item) keeps the four-product form.
+  // three real products per complex product (Karatsuba; sums of residues are exact mod m_i) instead of four: 25 % fewer int8
+  // operations for one more operand plane per side and one more residue plane.  An item then carries half the MMA work per
+  // accumulator, so short K (where the epilogue paces the item) keeps the four-product form: measured break-even K ~ 4096.
   const bool kara = ctx->crt_products == 3 || (ctx->crt_products == 0 && Kp >= ctx->crt_kara_min_k);
   const int TM = kara ? 2 * CRT_BT : CRT_BT;        // At rows per tile
   const int NPB = kara ? 3 : 2, NPR = kara ? 3 : 2;  // Bt operand planes, residue planes per modulus
@@ -841,7 +839,7 @@ int launch_k1_crt(tncb_ctx* ctx, const PairPlan& P, const double2* A, const doub
       if (items > 0x7fffffffLL) { cleanup(); return fail(TNCB_ERR_UNSUPPORTED, "too many work items"); }
       g.total_items = (int)items;
       g.group = ctx->crt_group;
-      for (int i = 0; i < CRT_MAX_MOD; i++) { g.mod[i] = T.mod[i]; g.magic[i] = T.magic[i]; }
+      for (int i = 0; i < CRT_MAX_MOD; i++) { g.negmod[i] = -T.mod[i]; g.magic[i] = T.magic[i]; }
       const int n_clusters = (int)std::min<long long>(n_clusters_max, items);
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3((unsigned)(2 * n_clusters)); cfg.blockDim = dim3(CRT_THREADS);

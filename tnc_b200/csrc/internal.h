@@ -56,6 +56,7 @@ struct Arena {
   int alloc(size_t bytes, void** out);
   void free(void* p, size_t bytes);
   void release_all();
+  size_t trim();             // cudaFree every slab that holds no live block; returns the bytes given back
 };
 
 } // namespace tncb
@@ -85,7 +86,7 @@ struct tncb_ctx {
   size_t crt_ws_bytes = (size_t)12 << 30; int crt_group = 8;
   double last_int8_ops = 0.0; int last_nmod = 0; int last_products = 0;
   int crt_products = 0;            // real int8 products per complex product: 0 = auto (3 when K >= crt_kara_min_k), 3, 4
-  long long crt_kara_min_k = 1024;
+  long long crt_kara_min_k = 4096;
   uint64_t engine_count[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // K0, K0 split-K, K1 DMMA, K1 DMMA split-K, K1' tcgen05, K2, permute, -
   // dominant-kernel timing: 0 off, 1 keep the last launch (gemm_ev0/1), 2 accumulate every launch (event pool)
   int time_gemm = 0; cudaEvent_t gemm_ev0 = nullptr, gemm_ev1 = nullptr; bool gemm_ev_valid = false;

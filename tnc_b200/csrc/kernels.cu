@@ -735,7 +735,24 @@ k2_kernel(const double2* __restrict__ Big, const double2* __restrict__ Sml, doub
     double ar[NS], ai[NS];
 #pragma unroll
     for (int sI = 0; sI < NS; sI++) { ar[sI] = 0.0; ai[sI] = 0.0; }
-    for (int k = 0; k < K; k++) {
+    // four loads of the big operand in flight per thread before their 16 NS DFMAs: with one load per trip the HBM latency
+    // was exposed (d12 Sycamore slices, NS = K = 16: 13.7 TFLOP/s = 3.4 TB/s, profiles/r02_trace_sycamore_d12_slice.txt)
+    int k = 0;
+    for (; k + 4 <= K; k += 4) {
+      double2 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) v[u] = __ldg(Big + off + s_kbig[k + u]);
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+#pragma unroll
+        for (int sI = 0; sI < NS; sI++) {
+          const double2 w = s_s[sI * K + k + u];   // broadcast
+          ar[sI] = fma(w.x, v[u].x, ar[sI]); ar[sI] = fma(-w.y, v[u].y, ar[sI]);
+          ai[sI] = fma(w.x, v[u].y, ai[sI]); ai[sI] = fma(w.y, v[u].x, ai[sI]);
+        }
+      }
+    }
+    for (; k < K; k++) {
       const double2 v = __ldg(Big + off + s_kbig[k]);
 #pragma unroll
       for (int sI = 0; sI < NS; sI++) {

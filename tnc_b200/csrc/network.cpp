@@ -357,7 +357,7 @@ struct OffsetAlloc {
   }
 };
 
-static void plan_static_layout(tncb_plan* P, int sm_count) {
+static void plan_static_layout(tncb_plan* P, int sm_count, size_t device_bytes) {
   Schedule& S = P->S;
   P->is_static = !S.steps.empty() && std::getenv("TNCB_NO_STATIC") == nullptr;
   for (int k : S.leaf_kind) if (k == TNCB_DATA_DEVICE) P->is_static = false;   // addresses change per call
@@ -412,7 +412,9 @@ static void plan_static_layout(tncb_plan* P, int sm_count) {
     }
   }
   P->ws_bytes = A.top;
-  size_t limit = (size_t)64 << 30;
+  // one workspace for all intermediates of a run: at most 64 GiB or 0.62 of the device (B200: ~110 GiB; leaves room for the
+  // int8 engine's 12 GiB of planes and the staged leaves), whichever is larger; TNCB_PLAN_WS_GB overrides
+  size_t limit = std::max((size_t)64 << 30, (size_t)(0.62 * (double)device_bytes));
   if (const char* e = std::getenv("TNCB_PLAN_WS_GB")) limit = (size_t)std::max(1, atoi(e)) << 30;
   if (P->ws_bytes > limit) { P->is_static = false; return; }
   // ---- batch descriptors ----
@@ -640,7 +642,9 @@ int tncb_plan_create(tncb_ctx* ctx, const tncb_tn* tn, const tncb_path* path, tn
   tncb_plan* p = new tncb_plan();
   int rc = tncb::build_schedule(tn, path, p->S);
   if (rc) { delete p; return rc; }
-  tncb::plan_static_layout(p, ctx ? ctx->sm_count : 148);
+  size_t dev_free = 0, dev_total = 0;
+  if (ctx) { cudaSetDevice(ctx->device); if (cudaMemGetInfo(&dev_free, &dev_total) != cudaSuccess) { dev_total = 0; cudaGetLastError(); } }
+  tncb::plan_static_layout(p, ctx ? ctx->sm_count : 148, dev_total);
   *out = p;
   return TNCB_OK;
 }

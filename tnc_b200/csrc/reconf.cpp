@@ -26,23 +26,27 @@ typedef unsigned __int128 u128;
 
 // Objective of one pair step from the log2 sizes of its operands (w1, w2) and of their shared legs (wk):
 //   flops mode:  2^(w1 + w2 - wk) + size_weight * 2^(w1 + w2 - 2 wk)
-//   time mode :  the device-time model of contractionpath/contraction_cost.py gpu_time_tensors (same constants, passed in)
+//   time mode :  the device-time model of contractionpath/contraction_cost.py gpu_time_mnk (same constants, passed in)
 struct Objective {
   bool time = false;
   double size_weight = 0.0;
-  double crt = 160e12, k_half = 600.0, dmma = 25e12, hbm = 5e12, launch = 5e-6;
+  double crt = 160e12, k_half = 600.0, dmma = 34e12, hbm = 5e12, launch = 5e-6, dmma_k_half = 12.0, crt_k_max = 1048576.0, conv = 40.0;
   double pair(double w1, double w2, double wk) const {
     if (!time) return std::exp2(w1 + w2 - wk) + (size_weight != 0.0 ? size_weight * std::exp2(w1 + w2 - 2.0 * wk) : 0.0);
+    // contraction_cost.gpu_time_mnk, term by term
     const double m = std::exp2(w1 - wk), n = std::exp2(w2 - wk), k = std::exp2(wk);
-    const double mnk = m * n * k;
-    const bool big = m >= 128.0 && n >= 128.0 && k >= 256.0 && mnk >= 268435456.0;
-    const double t_math = 8.0 * mnk / (big ? crt * k / (k + k_half) : dmma);
+    const double mnk = m * n * k, flops = 8.0 * mnk;
     const double t_mem = 16.0 * (m * k + n * k + m * n) / hbm;
-    return std::max(t_math, t_mem) + launch;
+    double t = std::max(flops / (dmma * k / (k + dmma_k_half)), t_mem);
+    if (m >= 128.0 && n >= 128.0 && k >= 256.0 && k <= crt_k_max && mnk >= 268435456.0) {
+      const double t_crt = flops / (crt * k / (k + k_half)) + conv * (m * k + n * k) / hbm;
+      t = std::min(t, std::max(t_crt, t_mem));
+    }
+    return t + launch;
   }
   void load(double sw, const double* tm) {
     size_weight = sw; time = tm != nullptr;
-    if (tm) { crt = tm[0]; k_half = tm[1]; dmma = tm[2]; hbm = tm[3]; launch = tm[4]; }
+    if (tm) { crt = tm[0]; k_half = tm[1]; dmma = tm[2]; hbm = tm[3]; launch = tm[4]; dmma_k_half = tm[5]; crt_k_max = tm[6]; conv = tm[7]; }
   }
 };
 

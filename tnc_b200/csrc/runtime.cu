@@ -76,6 +76,20 @@ void Arena::release_all() {
   slabs.clear(); reserved = live = 0;
 }
 
+size_t Arena::trim() {
+  size_t freed = 0;
+  for (size_t i = 0; i < slabs.size();) {
+    Slab& s = slabs[i];
+    if (s.free_by_off.size() == 1 && s.free_by_off.begin()->first == 0 && s.free_by_off.begin()->second == s.size) {
+      cudaFree(s.base);
+      freed += s.size; reserved -= s.size;
+      slabs.erase(slabs.begin() + i);
+    } else i++;
+  }
+  if (slabs.empty()) next_slab = (size_t)256 << 20;
+  return freed;
+}
+
 void gemm_timer_begin(tncb_ctx* ctx) {
   if (ctx->time_gemm == 1) cudaEventRecord(ctx->gemm_ev0, ctx->stream);
   else if (ctx->time_gemm == 2) {
@@ -243,6 +257,18 @@ int tncb_contract_pair_host(tncb_ctx* ctx, int n_a, const uint64_t* a_legs, cons
 }
 
 void* tncb_ctx_stream(tncb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int tncb_ctx_trim(tncb_ctx* ctx, uint64_t* freed_bytes, uint64_t* reserved_bytes) {
+  if (!ctx) return fail(TNCB_ERR_INVALID, "ctx is null");
+  TNCB_CUDA(cudaSetDevice(ctx->device));
+  TNCB_CUDA(cudaStreamSynchronize(ctx->stream));      // stream-ordered reuse: nothing may still be running in a freed block
+  for (auto& c : ctx->plan_cache) tncb_plan_destroy(c.plan);   // the internal plans behind tncb_contract_tensor_network
+  ctx->plan_cache.clear();
+  const size_t f = ctx->arena.trim();
+  if (freed_bytes) *freed_bytes = f;
+  if (reserved_bytes) *reserved_bytes = ctx->arena.reserved;
+  return TNCB_OK;
+}
 
 int tncb_ctx_stats(tncb_ctx* ctx, uint64_t* kernel_launches, uint64_t* arena_peak_bytes, uint64_t* arena_live_bytes) {
   if (!ctx) return fail(TNCB_ERR_INVALID, "ctx is null");
