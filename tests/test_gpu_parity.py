@@ -134,6 +134,29 @@ def test_pairs_k2_streaming_kernel(ctx, built_lib):
         check_pair(ctx, rng, a_legs, a_dims, b_legs, b_dims)
 
 
+def test_pairs_k2_large_operands(ctx, built_lib):
+    """K2 with >= 2^16 free elements on the big side (several grid-stride trips per thread): orientations, K = 1..16,
+    NS = 1..16, scattered K legs, odd dims and a ragged last block, against the oracle."""
+    from tnc_b200._lib import u64_array
+    rng = np.random.default_rng(43)
+    def cls(a_legs, a_dims, b_legs, b_dims):
+        return built_lib.tncb_pair_kernel_class(len(a_legs), u64_array(a_legs), u64_array(a_dims), len(b_legs), u64_array(b_legs), u64_array(b_dims))
+    cases = [
+        (list(range(20)), [2] * 20, [3, 17, 9, 12, 30, 31, 32, 33], [2] * 8),         # 2^16 x 16 x 16, big A, K legs scattered
+        ([3, 17, 9, 12, 30, 31, 32, 33], [2] * 8, list(range(20)), [2] * 20),         # same, big B
+        (list(range(19)), [2] * 19, [18, 17, 16, 40], [2, 2, 2, 2]),                  # K = 8 on the fastest legs, NS = 2
+        (list(range(18)), [2] * 18, [0, 40, 41, 42, 43], [2] * 5),                    # K = 2 on the slowest leg, NS = 16
+        ([0, 1, 2, 3], [37, 41, 7, 47], [2, 9], [7, 5]),                              # odd dims: BIG = 37*41*47 = 71299 (ragged block), K = 7, NS = 8 (5 used)
+        ([9, 2], [3, 11], [0, 1, 2, 3], [29, 53, 11, 59]),                            # big B, M = 3, K = 11
+        (list(range(17)), [2] * 17, [40], [13]),                                      # K = 1: outer product with a 2^17 operand, NS = 16 (13 used)
+    ]
+    for a_legs, a_dims, b_legs, b_dims in cases:
+        assert cls(a_legs, a_dims, b_legs, b_dims) == 2, (a_legs, b_legs)
+        ctx.reset_stats()
+        check_pair(ctx, rng, a_legs, a_dims, b_legs, b_dims)
+        assert ctx.engine_counts()["k2"] == 1
+
+
 @pytest.mark.parametrize("mode", ["interleaved", "a_suffix_b_prefix", "a_prefix_b_suffix", "reversed"])
 def test_pairs_k1_modes(ctx, mode):
     """K1 (gather + DMMA ZGEMM) under the four loader-mode combinations, dims 2 and 4."""

@@ -686,6 +686,11 @@ static int launch_k1(tncb_ctx* ctx, const PairPlan& P, const double2* A, const d
 // K2: streaming kernel for big x tiny pairs (HBM-bound).  thread <-> one index x of the big free
 // side; the tiny operand sits in shared memory as S[s][k]; every thread reads its K elements of the
 // big operand once and writes its NS outputs.  Algorithmic traffic 16*(BIG*K + BIG*SMALL) bytes.
+// Gate-sized tiny operands (K, NS <= 4) stream at 5.8-6.1 TB/s.  With K = NS = 16 (the stem steps of the Sycamore-53 depth-12
+// slices: 16 input and 16 output streams GBs apart per block) it stays at 3.2 TB/s / 35 % of the FP64 pipe although DRAM
+// moves exactly the algorithmic bytes in full sectors (profiles/r02_ncu_k2_summary.txt).  Two fixes for "not enough loads
+// in flight" were measured and removed again: four loads per trip (11.0 vs 10.8 ms) and a 3-stage cp.async ring in shared
+// memory with 48 loads in flight per thread (11.7-13.5 ms) -- so the limit is not load latency under this access pattern.
 // ------------------------------------------------------------------------------------------
 struct K2Args {
   LegList big;     // free legs of the big operand (strides in the big operand)
@@ -735,24 +740,7 @@ k2_kernel(const double2* __restrict__ Big, const double2* __restrict__ Sml, doub
     double ar[NS], ai[NS];
 #pragma unroll
     for (int sI = 0; sI < NS; sI++) { ar[sI] = 0.0; ai[sI] = 0.0; }
-    // four loads of the big operand in flight per thread before their 16 NS DFMAs: with one load per trip the HBM latency
-    // was exposed (d12 Sycamore slices, NS = K = 16: 13.7 TFLOP/s = 3.4 TB/s, profiles/r02_trace_sycamore_d12_slice.txt)
-    int k = 0;
-    for (; k + 4 <= K; k += 4) {
-      double2 v[4];
-#pragma unroll
-      for (int u = 0; u < 4; u++) v[u] = __ldg(Big + off + s_kbig[k + u]);
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-#pragma unroll
-        for (int sI = 0; sI < NS; sI++) {
-          const double2 w = s_s[sI * K + k + u];   // broadcast
-          ar[sI] = fma(w.x, v[u].x, ar[sI]); ar[sI] = fma(-w.y, v[u].y, ar[sI]);
-          ai[sI] = fma(w.x, v[u].y, ai[sI]); ai[sI] = fma(w.y, v[u].x, ai[sI]);
-        }
-      }
-    }
-    for (; k < K; k++) {
+    for (int k = 0; k < K; k++) {
       const double2 v = __ldg(Big + off + s_kbig[k]);
 #pragma unroll
       for (int sI = 0; sI < NS; sI++) {
