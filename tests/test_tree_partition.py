@@ -58,7 +58,7 @@ def test_gpu_time_model_is_two_roofed():
     big = gpu_time_tensors(Tensor([0, 1], [4096, 4096]), Tensor([1, 2], [4096, 4096]))         # compute bound, K1' rate
     assert abs(big - (8 * 4096 ** 3 / (160e12 * 4096 / 4696) + 40.0 * 2 * 4096 ** 2 / 5e12 + 5e-6)) < 1e-9
     far = gpu_time_tensors(Tensor([0, 1], [1 << 23, 128]), Tensor([0, 2], [1 << 23, 128]))      # K = 2^23: too long for K1' -> FP64 rate
-    assert abs(far - (8 * 128 * 128 * 2.0 ** 23 / (34e12 * 2.0 ** 23 / (2.0 ** 23 + 12)) + 5e-6)) < 1e-9
+    assert abs(far - (8 * 128 * 128 * 2.0 ** 23 / (34e12 * 2.0 ** 23 / (2.0 ** 23 + 24)) + 5e-6)) < 1e-9
     thin = gpu_time_tensors(Tensor([0, 1], [1 << 22, 2]), Tensor([1, 2], [2, 2]))                 # bandwidth bound
     assert abs(thin - (16.0 * ((1 << 23) + 4 + (1 << 23)) / 5e12 + 5e-6)) < 1e-12
     a, b = Tensor([0, 1], [1024, 1024]), Tensor([1, 2], [1024, 1024])

@@ -124,7 +124,7 @@ def communication_path_op_costs(inputs: Sequence[Tensor], path, only_count_ops: 
 # partitioned or sliced contraction are as often bandwidth-bound (tensors of 2^28..2^30 elements meeting tiny ones) as
 # compute-bound, and the fan-in moves them over NVLink.  `gpu_time_tensors` is a two-roof estimate per pair from measured
 # rates of this repo's kernels (profiles/r02_engine_sweep.jsonl, r02_trace_part*.txt, r02_trace_sycamore_d12_slice.txt):
-#   * FP64 kernels (K1 DMMA, K2, K0): 34 TFLOP/s x K/(K+12)  (35 at K = 2^23; 18.5 at K = 16; gate-sized K stay HBM-bound);
+#   * FP64 kernels (K1 DMMA, K2, K0): 34 TFLOP/s x K/(K+24)  (35 at K = 2^23; 12.5-18.5 at K = 16; gate-sized K stay HBM-bound);
 #   * K1' (int8 engine; M, N >= 128, 256 <= K <= 2^20, MNK >= 2^28): 160 K/(K+600) TFLOP/s-equivalent (48 at K=256, 74 at 512,
 #     124 at 2048, 140 at 4096: the residue / reconstruction passes do not shrink with K) plus the operand conversion,
 #     40 bytes of residue planes per operand element (what makes M = N = 128, K = 2^20 cost 3 ms more than its GEMM);
@@ -132,7 +132,7 @@ def communication_path_op_costs(inputs: Sequence[Tensor], path, only_count_ops: 
 # Used by tools/plan_partitions.py (partitionings) and csrc/reconf.cpp via tools/search_path.py (trees + slices): the C++
 # Objective::pair restates exactly this function and tests/test_tree_reconfiguration.py pins the two against each other.
 GPU_RATES = {"crt_flops": 160e12, "crt_k_half": 600.0, "dmma_flops": 34e12, "hbm_bytes": 5e12, "launch_s": 5e-6,
-             "dmma_k_half": 12.0, "crt_k_max": 1048576.0, "crt_conv_bytes": 40.0, "nvlink_bytes": 6e11, "hop_s": 30e-6}
+             "dmma_k_half": 24.0, "crt_k_max": 1048576.0, "crt_conv_bytes": 40.0, "nvlink_bytes": 6e11, "hop_s": 30e-6}
 
 
 def gpu_time_mnk(m: float, n: float, k: float) -> float:

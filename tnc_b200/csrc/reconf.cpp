@@ -30,7 +30,7 @@ typedef unsigned __int128 u128;
 struct Objective {
   bool time = false;
   double size_weight = 0.0;
-  double crt = 160e12, k_half = 600.0, dmma = 34e12, hbm = 5e12, launch = 5e-6, dmma_k_half = 12.0, crt_k_max = 1048576.0, conv = 40.0;
+  double crt = 160e12, k_half = 600.0, dmma = 34e12, hbm = 5e12, launch = 5e-6, dmma_k_half = 24.0, crt_k_max = 1048576.0, conv = 40.0;
   double pair(double w1, double w2, double wk) const {
     if (!time) return std::exp2(w1 + w2 - wk) + (size_weight != 0.0 ? size_weight * std::exp2(w1 + w2 - 2.0 * wk) : 0.0);
     // contraction_cost.gpu_time_mnk, term by term
