@@ -57,13 +57,17 @@ struct DeviceData {
 };
 
 struct TensorData {
-  enum Kind { Uncontracted, Gate, Matrix, Device } kind = Uncontracted;
+  enum Kind { Uncontracted, Gate, Matrix, Device, File } kind = Uncontracted;
+  std::string file_path;                                                     // File((path, adjoint)), HDF5 (io::hdf5)
   std::string gate_name; std::vector<double> angles; bool adjoint = false;   // Gate((name, angles, adjoint))
   std::vector<Complex64> matrix;                                             // Matrix (host, row-major)
   std::shared_ptr<DeviceData> device;                                        // Matrix resident on the GPU
 
   static TensorData gate(std::string name, std::vector<double> ang = {}, bool adj = false) {
     TensorData d; d.kind = Gate; d.gate_name = std::move(name); d.angles = std::move(ang); d.adjoint = adj; return d;
+  }
+  static TensorData file(std::string path, bool adj = false) {
+    TensorData d; d.kind = File; d.file_path = std::move(path); d.adjoint = adj; return d;
   }
   // TensorData::new_from_data(dimensions, data, None)  (tensordata.rs:31-37)
   static TensorData new_from_data(const std::vector<uint64_t>&, std::vector<Complex64> data) {
@@ -85,6 +89,7 @@ struct Tensor {
   bool is_leaf() const { return tensors.empty(); }
   bool is_composite() const { return !tensors.empty(); }
   void set_tensor_data(TensorData d) { tensordata = std::move(d); }
+  void push_tensor(Tensor t) { tensors.push_back(std::move(t)); }
   const Tensor& tensor(size_t i) const { return tensors.at(i); }
 
   // `elements()`: row-major data of a contracted leaf (downloads from the device)
@@ -129,6 +134,8 @@ struct Marshal {  // owns every buffer the C structs point into
         n.kind = TNCB_DATA_MATRIX; n.host_re_im = reinterpret_cast<const double*>(t.tensordata.matrix.data()); break;
       case TensorData::Device:
         n.kind = TNCB_DATA_DEVICE; n.device = t.tensordata.device->t; break;
+      case TensorData::File:
+        n.kind = TNCB_DATA_FILE; n.file_path = t.tensordata.file_path.c_str(); n.file_adjoint = t.tensordata.adjoint; break;
       default: n.kind = TNCB_DATA_UNCONTRACTED;
     }
     return n;
@@ -215,5 +222,62 @@ class NetworkPlan {
   Context& ctx_;
   tncb_plan* h_ = nullptr;
 };
+
+// tnc::io::hdf5 (tnc/src/io/hdf5.rs): /tensors/<name> datasets with `bids` attributes, "-1" = the output tensor.
+namespace io { namespace hdf5 {
+namespace detail {
+struct File {
+  tncb_h5file* h = nullptr;
+  explicit File(const std::string& path) { check(tncb_hdf5_open(path.c_str(), nullptr, &h)); }
+  ~File() { tncb_hdf5_close(h); }
+  File(const File&) = delete;
+  File& operator=(const File&) = delete;
+  std::vector<uint64_t> bids(size_t i) const {
+    size_t n = 0;
+    check(tncb_hdf5_attr(h, i, "bids", 0, nullptr, &n));
+    std::vector<int64_t> v(n ? n : 1);
+    check(tncb_hdf5_attr(h, i, "bids", n, v.data(), &n));
+    std::vector<uint64_t> out;
+    for (size_t q = 0; q < n; q++) { if (v[q] < 0) throw Error(TNCB_ERR_INVALID, "negative bond id"); out.push_back((uint64_t)v[q]); }
+    return out;
+  }
+  std::vector<Complex64> read(size_t i, std::vector<uint64_t>* shape) const {
+    int rank = 0; uint64_t dims[32], elems = 0;
+    check(tncb_hdf5_shape(h, i, &rank, dims, &elems));
+    shape->assign(dims, dims + rank);
+    std::vector<Complex64> data(elems);
+    if (elems) check(tncb_hdf5_read(h, i, reinterpret_cast<double*>(data.data())));
+    return data;
+  }
+};
+}  // namespace detail
+
+// load_tensor (hdf5.rs:28-34, 54-88): a composite of Matrix leaves in member order; legs = the `bids` of "-1"
+inline Tensor load_tensor(const std::string& filename) {
+  detail::File f(filename);
+  Tensor tn;
+  bool have_out = false;
+  for (size_t i = 0; i < tncb_hdf5_count(f.h); i++) {
+    if (std::string(tncb_hdf5_name(f.h, i)) == "-1") { tn.legs = f.bids(i); have_out = true; continue; }
+    std::vector<uint64_t> shape;
+    std::vector<Complex64> data = f.read(i, &shape);
+    Tensor t(f.bids(i), shape);
+    t.set_tensor_data(TensorData::new_from_data(shape, std::move(data)));
+    tn.push_tensor(std::move(t));
+  }
+  if (!have_out) throw Error(TNCB_ERR_IO, "no output tensor '-1' in /tensors");
+  return tn;
+}
+// load_data (hdf5.rs:37-43, 90-103): the first member of /tensors
+inline std::vector<Complex64> load_data(const std::string& filename, std::vector<uint64_t>* shape) {
+  detail::File f(filename);
+  if (tncb_hdf5_count(f.h) == 0) throw Error(TNCB_ERR_IO, "no member in /tensors");
+  return f.read(0, shape);
+}
+// store_data (hdf5.rs:46-52, 105-113)
+inline void store_data(const std::string& filename, const std::vector<uint64_t>& shape, const std::vector<Complex64>& data) {
+  check(tncb_hdf5_store_data(filename.c_str(), (int)shape.size(), shape.data(), reinterpret_cast<const double*>(data.data())));
+}
+}}  // namespace io::hdf5
 
 }  // namespace tnc

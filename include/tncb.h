@@ -45,12 +45,14 @@ typedef enum tncb_status {
   TNCB_ERR_CUDA = -6,         /* CUDA runtime error (tncb_last_error has the text)   */
   TNCB_ERR_GATE = -7,         /* unknown gate / wrong angle count (gates.rs:54,103)  */
   TNCB_ERR_NCCL = -8,         /* NCCL error or libnccl not loadable                  */
-  TNCB_ERR_UNSUPPORTED = -9   /* e.g. TensorData::File payloads (no HDF5)            */
+  TNCB_ERR_UNSUPPORTED = -9,  /* e.g. an HDF5 feature outside the supported subset     */
+  TNCB_ERR_IO = -10           /* file missing / unreadable / not (well-formed) HDF5    */
 } tncb_status;
 
 typedef struct tncb_ctx tncb_ctx;       /* one device + stream + arena              */
 typedef struct tncb_tensor tncb_tensor; /* a device-resident complex128 tensor      */
 typedef struct tncb_plan tncb_plan;     /* a compiled (network, path) schedule      */
+typedef struct tncb_h5file tncb_h5file; /* an opened HDF5 tensor file (host only)   */
 
 const char* tncb_strerror(int status);
 /* Text of the last error raised on this thread (CUDA/NCCL message, offending pair). */
@@ -207,7 +209,8 @@ typedef enum tncb_data_kind {
   TNCB_DATA_UNCONTRACTED = 0, /* TensorData::Uncontracted (composite or empty slot) */
   TNCB_DATA_MATRIX = 1,       /* TensorData::Matrix: host_re_im, row-major          */
   TNCB_DATA_GATE = 2,         /* TensorData::Gate((name, angles, adjoint))          */
-  TNCB_DATA_DEVICE = 3        /* already on the device (consumed by the call)       */
+  TNCB_DATA_DEVICE = 3,       /* already on the device (consumed by the call)       */
+  TNCB_DATA_FILE = 4          /* TensorData::File((path, adjoint)): HDF5, see below */
 } tncb_data_kind;
 
 typedef struct tncb_tn {
@@ -224,6 +227,11 @@ typedef struct tncb_tn {
   int n_gate_angles;
   int gate_adjoint;
   tncb_tensor* device;
+  /* TNCB_DATA_FILE (tensordata.rs:43-49): the first member of the file's /tensors group is loaded while the leaves are
+   * staged (load_data, io/hdf5.rs:37-43), adjointed when file_adjoint != 0 (halves of the dims swapped + conjugated,
+   * gates.rs:82-99; the rank must then be a power of two) and must have exactly this leaf's dims -> TNCB_ERR_SHAPE. */
+  const char* file_path;
+  int file_adjoint;
 } tncb_tn;
 
 typedef struct tncb_path {
@@ -275,6 +283,38 @@ int tncb_plan_run_slices(tncb_ctx* ctx, tncb_plan* plan, size_t first, size_t st
 int tncb_plan_info(const tncb_plan* plan, uint64_t* n_pairs, double* flops, double* bytes,
                    uint64_t* peak_bytes, uint64_t* n_kernels);
 void tncb_plan_destroy(tncb_plan* plan);
+
+/* ---- HDF5 tensor files: replaces tnc::io::hdf5 (tnc/src/io/hdf5.rs), which binds libhdf5 through hdf5-metno.
+ *      Neither is available here; csrc/hdf5io.cpp restates the published file format for the subset those calls produce
+ *      and read (old- and new-style groups, object headers 1/2, contiguous / compact / chunked data with deflate and
+ *      shuffle, Complex = compound of two floats, integer attributes).  Host only, no GPU needed.  Layout (hdf5.rs:1-15):
+ *      one group `tensors`, one dataset per tensor (its shape = the bond dimensions), integer attribute `bids` = the
+ *      bond ids; the dataset named "-1" carries the network's open bonds in `bids` and no data. ---- */
+/* File::open + group(`group`), NULL = "/tensors".  Members are listed in ascending name order (strcmp), the order of
+ * Group::member_names (H5Literate by name), so "-1" < "0" < "1" < "10" < "2". */
+int tncb_hdf5_open(const char* path, const char* group, tncb_h5file** out);
+void tncb_hdf5_close(tncb_h5file* file);
+size_t tncb_hdf5_count(const tncb_h5file* file);
+const char* tncb_hdf5_name(const tncb_h5file* file, size_t i);      /* NULL when i is out of range */
+/* Shape of member i (dims needs room for 32 entries); any of rank / dims / elems may be NULL. */
+int tncb_hdf5_shape(const tncb_h5file* file, size_t i, int* rank, uint64_t* dims, uint64_t* elems);
+/* Integer attribute (`bids`, `tids`) of member i, widened to int64 (Attribute::read_1d, hdf5.rs:61,70).
+ * out == NULL: only *n is set. */
+int tncb_hdf5_attr(const tncb_h5file* file, size_t i, const char* name, size_t cap, int64_t* out, size_t* n);
+/* read_dyn::<Complex64> (hdf5.rs:71,96): row-major interleaved re/im doubles.  Compounds of two f32 / big-endian floats
+ * are converted; a real floating-point dataset is widened with zero imaginary parts (extension). */
+int tncb_hdf5_read(const tncb_h5file* file, size_t i, double* out_re_im);
+/* TensorData::File((path, adjoint)).into_data() (tensordata.rs:43-49) on the host: load_data(path) = the first member of
+ * /tensors, then matrix_adjoint_inplace when adjoint != 0; the result must have exactly rank / dims (-> TNCB_ERR_SHAPE).
+ * This is the routine the network executors call for TNCB_DATA_FILE leaves. */
+int tncb_hdf5_load_leaf(const char* path, int adjoint, int rank, const uint64_t* dims, double* out_re_im);
+/* store_data (hdf5.rs:46-52,105-113): a new file with /tensors/-1 = the tensor. */
+int tncb_hdf5_store_data(const char* path, int rank, const uint64_t* dims, const double* data_re_im);
+/* A whole network file in the layout read_tensor expects (the reference builds such files only in its tests,
+ * hdf5.rs:141-170): n datasets, data_re_im[i] == NULL declares a dataset without data, n_bids[i] < 0 (or n_bids == NULL)
+ * omits the attribute. */
+int tncb_hdf5_store(const char* path, size_t n, const char* const* names, const int* ranks, const uint64_t* const* dims,
+                    const double* const* data_re_im, const int64_t* n_bids, const uint64_t* const* bids);
 
 /* ---- partitioned fan-in: replaces tnc::mpi::communication
  *      (scatter_tensor_network :125-195, intermediate_reduce_tensor_network :199-249).

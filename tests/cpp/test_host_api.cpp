@@ -1,8 +1,10 @@
 // C++ host-API tests over libtncb200, written to read like the reference's own tests
 // (tnc/src/tensornetwork/contraction.rs:226-264, io/qasm/qasm_importer.rs:171-194,
-// builders/circuit_builder.rs:372-396).  Needs a GPU; run by tests/test_gpu_cpp_host.py.
+// builders/circuit_builder.rs:372-396, io/hdf5.rs:196-257).  Needs a GPU; run by tests/test_gpu_cpp_host.py.
+// `test_host_api --io <dir>` runs only the HDF5 tests, which need no GPU (tests/test_gpu_cpp_host.py::test_cpp_hdf5_io).
 #include <cmath>
 #include <cstdio>
+#include <cstring>
 #include "tnc.hpp"
 
 using namespace tnc;
@@ -89,9 +91,59 @@ static void test_plan_and_repeated_calls(Context& ctx) {
   ctx.set_tolerance(1e-10); ctx.set_tolerance(0.0);
 }
 
-int main() {
+// io/hdf5.rs:238-257 (test_write_read), :214-236 (test_load_tensor through a file this library wrote)
+static void test_hdf5_write_read(const std::string& dir) {
+  const std::vector<Complex64> data = {{1, 0}, {0, -2}, {-3, 0}, {-2, -1}, {0, 0}, {0.5, 2}};
+  io::hdf5::store_data(dir + "/wr.h5", {2, 3}, data);
+  std::vector<uint64_t> shape;
+  auto read = io::hdf5::load_data(dir + "/wr.h5", &shape);
+  EXPECT((shape == std::vector<uint64_t>{2, 3}));
+  EXPECT(read == data);
+  // a network file: "0" = [[1, 2i], [3, i]] with bids [0, 1]; "-1" without data, bids [0, 1]
+  const std::vector<Complex64> m = {{1, 0}, {0, 2}, {3, 0}, {0, 1}};
+  const char* names[2] = {"-1", "0"};
+  const int ranks[2] = {0, 2};
+  const uint64_t d0[2] = {2, 2}, bids[2] = {0, 1};
+  const uint64_t* dims[2] = {nullptr, d0};
+  const double* payload[2] = {nullptr, reinterpret_cast<const double*>(m.data())};
+  const int64_t n_bids[2] = {2, 2};
+  const uint64_t* all_bids[2] = {bids, bids};
+  check(tncb_hdf5_store((dir + "/net.h5").c_str(), 2, names, ranks, dims, payload, n_bids, all_bids));
+  Tensor tn = io::hdf5::load_tensor(dir + "/net.h5");
+  EXPECT((tn.legs == std::vector<uint64_t>{0, 1}));
+  EXPECT(tn.tensors.size() == 1);
+  EXPECT((tn.tensor(0).legs == std::vector<uint64_t>{0, 1}) && (tn.tensor(0).bond_dims == std::vector<uint64_t>{2, 2}));
+  EXPECT(tn.tensor(0).elements() == m);
+  bool threw = false;
+  try { io::hdf5::load_data(dir + "/missing.h5", &shape); } catch (const Error& e) { threw = e.status == TNCB_ERR_IO; }
+  EXPECT(threw);
+}
+
+// TensorData::File leaves (tensordata.rs:43-49) inside contract_tensor_network
+static void test_file_leaf(Context& ctx, const std::string& dir) {
+  const std::vector<Complex64> a = {{1, 0}, {2, 5}, {3, -1}}, b = {{-4, 2}, {0, -1}};
+  io::hdf5::store_data(dir + "/a.h5", {3}, a);
+  Tensor t1({0}, {3}), t2({1}, {2});
+  t1.set_tensor_data(TensorData::file(dir + "/a.h5"));
+  t2.set_tensor_data(TensorData::new_from_data({2}, b));
+  Tensor result = contract_tensor_network(ctx, Tensor::new_composite({t1, t2}), ContractionPath::single(0, 1));
+  const Complex64 ref[6] = {{-4, 2}, {-18, -16}, {-10, 10}, {0, -1}, {5, -2}, {-1, -3}};
+  auto e = result.elements();
+  for (int i = 0; i < 6; i++) EXPECT(e[i] == ref[i]);
+}
+
+int main(int argc, char** argv) {
+  const std::string dir = argc > 2 ? argv[2] : "/tmp";
+  if (argc > 1 && std::strcmp(argv[1], "--io") == 0) {
+    try { test_hdf5_write_read(dir); } catch (const Error& e) { std::printf("FAIL uncaught tnc::Error %d: %s\n", e.status, e.what()); return 2; }
+    if (failures) { std::printf("%d failure(s)\n", failures); return 1; }
+    std::printf("HOST_IO_OK\n");
+    return 0;
+  }
   try {
     Context ctx(0);
+    test_hdf5_write_read(dir);
+    test_file_leaf(ctx, dir);
     test_outer_product_contraction(ctx);
     test_bell_contract(ctx);
     test_hadamards_amplitude(ctx);
@@ -100,6 +152,6 @@ int main() {
     test_plan_and_repeated_calls(ctx);
   } catch (const Error& e) { std::printf("FAIL uncaught tnc::Error %d: %s\n", e.status, e.what()); return 2; }
   if (failures) { std::printf("%d failure(s)\n", failures); return 1; }
-  std::printf("HOST_API_OK 6 tests\n");
+  std::printf("HOST_API_OK 8 tests\n");
   return 0;
 }

@@ -1,0 +1,101 @@
+"""TensorData::File leaves through contract_tensor_network on the device (tensordata.rs:43-49 inside contraction.rs:66-76):
+the library loads the HDF5 payloads while it stages the leaves, so a network whose gates come from files must give the same
+amplitude as the same network with in-memory payloads -- bit for bit, because the schedule and the staged bytes are equal."""
+import numpy as np
+import pytest
+
+from oracle import tnc_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _greedy(tn):
+    from tnc_b200.contractionpath.paths import Cotengrust
+    opt = Cotengrust(tn)
+    opt.find_path()
+    return opt.get_best_replace_path()
+
+
+def _variants(tmp_path):
+    """the same 12-qubit random-circuit amplitude network three times: gate leaves / Matrix leaves / File leaves (every
+    third file stored adjointed and flagged adjoint, which must undo itself)"""
+    from tnc_b200.builders import random_circuit
+    from tnc_b200.gates import load_gate, load_gate_adjoint
+    from tnc_b200.io import hdf5
+    from tnc_b200.tensornetwork import Tensor, TensorData
+    tn = random_circuit(12, 8, 0.5, 0.5, np.random.default_rng(77))
+    mats, files = [], []
+    for i, t in enumerate(tn.tensors):
+        td = t.tensordata
+        if td.kind == "gate":
+            name, ang, adj = td.gate
+            m = (load_gate_adjoint if adj else load_gate)(name, ang)
+        else:
+            m = np.asarray(td.matrix, dtype=np.complex128)
+        m = m.reshape(t.bond_dims)
+        mt = Tensor.new(t.legs, t.bond_dims); mt.set_tensor_data(TensorData.Matrix(m)); mats.append(mt)
+        ft = Tensor.new(t.legs, t.bond_dims)
+        p = str(tmp_path / ("leaf%d.h5" % i))
+        r = m.ndim
+        if i % 3 == 0 and r in (2, 4):           # store the adjoint, flag the leaf adjoint: into_data adjoints it back
+            stored = np.conj(np.transpose(m, list(range(r // 2, r)) + list(range(r // 2))))
+            hdf5.store_data(p, stored)
+            ft.set_tensor_data(TensorData.File(p, True))
+        else:
+            hdf5.store_data(p, m)
+            ft.set_tensor_data(TensorData.File(p, False))
+        files.append(ft)
+    return tn, Tensor.new_composite(mats), Tensor.new_composite(files)
+
+
+def test_file_leaves_equal_matrix_leaves(ctx, tmp_path):
+    from tnc_b200.tensornetwork import contract_tensor_network
+    tn, mat_tn, file_tn = _variants(tmp_path)
+    path = _greedy(tn)
+    a_gate = complex(contract_tensor_network(tn, path, ctx=ctx).to_numpy())
+    a_mat = complex(contract_tensor_network(mat_tn, path, ctx=ctx).to_numpy())
+    a_file = complex(contract_tensor_network(file_tn, path, ctx=ctx).to_numpy())
+    a_file2 = complex(contract_tensor_network(file_tn, path, ctx=ctx).to_numpy())      # second call: cached plan, files re-read
+    assert a_mat == a_gate and a_file == a_mat and a_file2 == a_mat
+    # against the oracle on the in-memory variant
+    def to_o(t):
+        if t.is_composite():
+            return orc.OTensor(children=[to_o(c) for c in t.tensors])
+        return orc.OTensor(list(t.legs), list(t.bond_dims), np.asarray(t.tensordata.matrix))
+    ref = complex(orc.contract_tensor_network(to_o(mat_tn), orc.OPath(list(path.toplevel), {})).data)
+    assert abs(a_file - ref) <= 1e-9 * abs(ref) + 1e-18
+
+
+def test_file_leaf_errors_leave_the_call_clean(ctx, tmp_path):
+    from tnc_b200 import TncbError
+    from tnc_b200.io import hdf5
+    from tnc_b200.tensornetwork import Tensor, TensorData, contract_tensor_network
+    from tnc_b200.contractionpath import ContractionPath
+    rng = np.random.default_rng(1)
+    a = rng.uniform(-1, 1, (2, 4)) + 1j * rng.uniform(-1, 1, (2, 4))
+    b = rng.uniform(-1, 1, (4, 3)) + 1j * rng.uniform(-1, 1, (4, 3))
+    hdf5.store_data(tmp_path / "a.h5", a)
+    ta = Tensor.new([0, 1], [2, 4]); ta.set_tensor_data(TensorData.File(str(tmp_path / "a.h5"), False))
+    tb = Tensor.new([1, 2], [4, 3]); tb.set_tensor_data(TensorData.Matrix(b))
+    path = ContractionPath.simple([(0, 1)])
+    got = contract_tensor_network(Tensor.new_composite([ta, tb]), path, ctx=ctx)
+    assert got.legs == [2, 0]                                    # (b \ a) ++ (a \ b), tensor.rs:463-479
+    np.testing.assert_allclose(got.to_numpy(), np.einsum("ik,kj->ji", a, b), rtol=0, atol=1e-14)
+    # a missing file: `load_data(filename).unwrap()` panics in the reference, here TNCB_ERR_IO
+    tm = Tensor.new([0, 1], [2, 4]); tm.set_tensor_data(TensorData.File(str(tmp_path / "missing.h5"), False))
+    with pytest.raises(TncbError) as e:
+        contract_tensor_network(Tensor.new_composite([tm, tb]), path, ctx=ctx)
+    assert e.value.status == -10
+    # a file whose shape is not the leaf's bond dimensions
+    hdf5.store_data(tmp_path / "wrong.h5", a.reshape(4, 2))
+    tw = Tensor.new([0, 1], [2, 4]); tw.set_tensor_data(TensorData.File(str(tmp_path / "wrong.h5"), False))
+    with pytest.raises(TncbError) as e:
+        contract_tensor_network(Tensor.new_composite([tw, tb]), path, ctx=ctx)
+    assert e.value.status == -2
+    # ... which the adjoint flag turns into the right shape: conj(a.reshape(4, 2)).T has dims [2, 4]
+    tw.set_tensor_data(TensorData.File(str(tmp_path / "wrong.h5"), True))
+    got = contract_tensor_network(Tensor.new_composite([tw, tb]), path, ctx=ctx)
+    np.testing.assert_allclose(got.to_numpy(), np.einsum("ik,kj->ji", np.conj(a.reshape(4, 2)).T, b), rtol=0, atol=1e-14)
+    # the context is still usable after the failures
+    got = contract_tensor_network(Tensor.new_composite([ta, tb]), path, ctx=ctx)
+    np.testing.assert_allclose(got.to_numpy(), np.einsum("ik,kj->ji", a, b), rtol=0, atol=1e-14)

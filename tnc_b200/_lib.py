@@ -32,6 +32,8 @@ TncbTn._fields_ = [
     ("n_gate_angles", C.c_int),
     ("gate_adjoint", C.c_int),
     ("device", C.c_void_p),
+    ("file_path", C.c_char_p),
+    ("file_adjoint", C.c_int),
 ]
 
 
@@ -112,6 +114,17 @@ SIGNATURES = {
     "tncb_comm_allreduce_sum": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tncb_comm_destroy": (C.c_int, [C.c_void_p]),
     "tncb_fanin_mapping": (C.c_int, [C.c_size_t, u64p, C.c_size_t, u64p, C.c_int, i32p]),
+    "tncb_hdf5_open": (C.c_int, [C.c_char_p, C.c_char_p, vpp]),
+    "tncb_hdf5_close": (None, [C.c_void_p]),
+    "tncb_hdf5_count": (C.c_size_t, [C.c_void_p]),
+    "tncb_hdf5_name": (C.c_char_p, [C.c_void_p, C.c_size_t]),
+    "tncb_hdf5_shape": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_int), u64p, u64p]),
+    "tncb_hdf5_attr": (C.c_int, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t, C.POINTER(C.c_int64), C.POINTER(C.c_size_t)]),
+    "tncb_hdf5_read": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p]),
+    "tncb_hdf5_load_leaf": (C.c_int, [C.c_char_p, C.c_int, C.c_int, u64p, C.c_void_p]),
+    "tncb_hdf5_store_data": (C.c_int, [C.c_char_p, C.c_int, u64p, C.c_void_p]),
+    "tncb_hdf5_store": (C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(C.c_char_p), C.POINTER(C.c_int), C.POINTER(u64p),
+                                  C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(u64p)]),
 }
 
 _lib = None
@@ -144,7 +157,7 @@ def lib() -> C.CDLL:
 def check(status: int) -> None:
     if status != 0:
         l = lib()
-        msg = l.tncb_last_error().decode() or l.tncb_strerror(status).decode()
+        msg = l.tncb_last_error().decode("utf-8", "replace") or l.tncb_strerror(status).decode()
         raise TncbError(status, msg)
 
 

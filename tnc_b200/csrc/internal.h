@@ -158,6 +158,9 @@ int k0_batch_fill(int sm_count, const PairPlan& p, K0BatchItem* item);   // retu
 int launch_k0_batch(tncb_ctx* ctx, const K0BatchItem* d_items, const int* d_block_start, int n_items, int total_blocks, char* ws);
 
 int tensor_new(tncb_ctx* ctx, int rank, const uint64_t* dims, tncb_tensor** out);
+
+// TensorData::File leaf (hdf5io.cpp): first member of /tensors, optionally adjointed, checked against the leaf's dims
+namespace h5 { int load_file_leaf(const char* path, bool adjoint, int rank, const uint64_t* dims, double* out_re_im); }
 } // namespace tncb
 
 #define TNCB_CUDA(call)                                                                   \

@@ -72,8 +72,10 @@ static int add_leaf(const tncb_tn* leaf, Schedule& S, size_t leaf_idx, int* slot
   } else if (leaf->kind == TNCB_DATA_DEVICE) {
     if (!leaf->device) return fail(TNCB_ERR_INVALID, "device leaf without a tensor handle");
     if (leaf->device->elems != m.elems) return fail(TNCB_ERR_SHAPE, "device leaf: element count mismatch");
+  } else if (leaf->kind == TNCB_DATA_FILE) {
+    if (!leaf->file_path) return fail(TNCB_ERR_INVALID, "file leaf without a path");
   } else {
-    return fail(TNCB_ERR_UNSUPPORTED, "unsupported TensorData kind (File payloads need HDF5)");
+    return fail(TNCB_ERR_INVALID, "unknown TensorData kind " + std::to_string(leaf->kind));
   }
   if (leaf->kind != TNCB_DATA_DEVICE) {
     S.leaf_offset[leaf_idx] = S.leaf_block_elems;
@@ -174,6 +176,7 @@ static int validate_leaves(const Schedule& S, const std::vector<const tncb_tn*>&
       if (lf->dims[i] != m->dims[i]) return fail(TNCB_ERR_SHAPE, "leaf " + std::to_string(li) + ": bond dimensions differ from the plan");
     if (lf->kind == TNCB_DATA_MATRIX && !lf->host_re_im) return fail(TNCB_ERR_INVALID, "matrix leaf " + std::to_string(li) + " without host data");
     if (lf->kind == TNCB_DATA_GATE && !lf->gate_name) return fail(TNCB_ERR_GATE, "gate leaf " + std::to_string(li) + " without a name");
+    if (lf->kind == TNCB_DATA_FILE && !lf->file_path) return fail(TNCB_ERR_INVALID, "file leaf " + std::to_string(li) + " without a path");
     if (lf->kind == TNCB_DATA_DEVICE) {
       if (!lf->device || !lf->device->ptr) return fail(TNCB_ERR_UNCONTRACTED, "device leaf " + std::to_string(li) + " without a tensor handle (already consumed?)");
       if (lf->device->elems != m->elems) return fail(TNCB_ERR_SHAPE, "device leaf " + std::to_string(li) + ": element count mismatch");
@@ -186,6 +189,8 @@ static int validate_leaves(const Schedule& S, const std::vector<const tncb_tn*>&
           return fail(TNCB_ERR_INVALID, "the same device tensor is passed as two leaves");
   return TNCB_OK;
 }
+
+static int stage_leaves(const Schedule& S, const std::vector<const tncb_tn*>& leaves, std::complex<double>* stage);
 
 // `resident` != nullptr: the leaf block already sits on the device (tncb_plan_stage); `tn` may then be null.
 static int execute(tncb_ctx* ctx, const Schedule& S, const tncb_tn* tn, tncb_tensor** out, int* n_out, uint64_t* out_legs,
@@ -207,18 +212,7 @@ static int execute(tncb_ctx* ctx, const Schedule& S, const tncb_tn* tn, tncb_ten
       // the previous network's upload may still be reading the staging buffer
       TNCB_CUDA(cudaStreamSynchronize(ctx->stream));
     }
-    std::complex<double>* stage = (std::complex<double>*)ctx->stage_host;
-    for (size_t li = 0; li < leaves.size(); li++) {
-      const tncb_tn* lf = leaves[li];
-      if (S.leaf_kind[li] != lf->kind) return fail(TNCB_ERR_INVALID, "network payload kinds do not match the plan");
-      if (lf->kind == TNCB_DATA_GATE) {
-        int cnt = gate_matrix(lf->gate_name, lf->gate_angles, lf->n_gate_angles, lf->gate_adjoint != 0, stage + S.leaf_offset[li]);
-        if (cnt < 0) return cnt;
-      } else if (lf->kind == TNCB_DATA_MATRIX) {
-        uint64_t e = 1; for (int i = 0; i < lf->rank; i++) e *= lf->dims[i];
-        std::memcpy(stage + S.leaf_offset[li], lf->host_re_im, e * sizeof(double2));
-      }
-    }
+    { int src = stage_leaves(S, leaves, (std::complex<double>*)ctx->stage_host); if (src) return src; }
     int rc = ctx->arena.alloc(block_bytes, &leaf_block);
     if (rc) return rc;
     TNCB_CUDA(cudaMemcpyAsync(leaf_block, ctx->stage_host, block_bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -449,6 +443,9 @@ static int stage_leaves(const Schedule& S, const std::vector<const tncb_tn*>& le
     } else if (lf->kind == TNCB_DATA_MATRIX) {
       uint64_t e = 1; for (int i = 0; i < lf->rank; i++) e *= lf->dims[i];
       std::memcpy(stage + S.leaf_offset[li], lf->host_re_im, e * sizeof(double2));
+    } else if (lf->kind == TNCB_DATA_FILE) {      // into_data for TensorData::File (tensordata.rs:43-49)
+      int rc = h5::load_file_leaf(lf->file_path, lf->file_adjoint != 0, lf->rank, lf->dims, (double*)(stage + S.leaf_offset[li]));
+      if (rc) return rc;
     }
   }
   return TNCB_OK;

@@ -124,6 +124,7 @@ const char* tncb_strerror(int status) {
     case TNCB_ERR_GATE: return "gate error";
     case TNCB_ERR_NCCL: return "NCCL error";
     case TNCB_ERR_UNSUPPORTED: return "unsupported";
+    case TNCB_ERR_IO: return "file error";
     default: return "unknown status";
   }
 }

@@ -6,6 +6,7 @@ upload and every pair kernel run inside libtncb200."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional
 
 import numpy as np
@@ -23,7 +24,8 @@ _KIND = {"uncontracted": 0, "matrix": 1, "gate": 2, "device": 3}
 # column-wise instead of one ctypes object per leaf (the 36-qubit bench network has 489 leaves per call)
 _TN_DTYPE = np.dtype([("n_children", np.uint64), ("children", np.uint64), ("rank", np.int32), ("legs", np.uint64), ("dims", np.uint64),
                       ("kind", np.int32), ("host_re_im", np.uint64), ("gate_name", np.uint64), ("gate_angles", np.uint64),
-                      ("n_gate_angles", np.int32), ("gate_adjoint", np.int32), ("device", np.uint64)], align=True)
+                      ("n_gate_angles", np.int32), ("gate_adjoint", np.int32), ("device", np.uint64),
+                      ("file_path", np.uint64), ("file_adjoint", np.int32)], align=True)
 assert _TN_DTYPE.itemsize == C.sizeof(TncbTn), "TncbTn layout drifted"
 _GATE_NAMES = {}
 
@@ -98,8 +100,12 @@ class _Marshal:
                     self.keep.append(arr)
                     rec[i]["kind"] = 1
                     rec[i]["host_re_im"] = arr.ctypes.data
-            elif k == "file":
-                rec[i]["kind"] = 99  # TensorData::File needs HDF5 -> TNCB_ERR_UNSUPPORTED
+            elif k == "file":   # TensorData::File((path, adjoint)): loaded by the library while it stages the leaves
+                buf = C.create_string_buffer(os.fsencode(td.file[0]))
+                self.keep.append(buf)
+                rec[i]["kind"] = 4
+                rec[i]["file_path"] = C.addressof(buf)
+                rec[i]["file_adjoint"] = int(bool(td.file[1]))
         return rec.ctypes.data
 
     def tn(self, t: Tensor) -> TncbTn:
