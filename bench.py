@@ -402,6 +402,11 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def all_ranks_ok(ok: bool) -> bool:
+        """True only if every rank says so: a leg that failed on ONE rank must be abandoned by ALL ranks together, or the
+        others would wait for it inside the next collective until the driver's clock runs out."""
+        return max_over_ranks(0.0 if ok else 1.0) == 0.0
+
     tn = build_network()                                  # same seed on every rank -> same network
     fpath = greedy_path(tn)
     if world == 1:
@@ -544,7 +549,8 @@ def run_ours(args):
             extras["sliced8_on_1gpu"] = {"ms_per_step": e0.elapsed_time(e1) / 3, "vs_flat": e0.elapsed_time(e1) / 3 / ms_per_step,
                                          "rel_diff_vs_flat": abs(samp - amp) / abs(amp), "sliced_legs": [int(l) for l in legs]}
         if world > 1:
-            extras["parity_n"] = parity_and_modes(tb, ctx, dist, torch, stream, tn, fpath, net, path, amp, rank, world, local, meta_group, max_over_ranks)
+            extras["parity_n"] = parity_and_modes(tb, ctx, dist, torch, stream, tn, fpath, net, path, amp, rank, world, local, meta_group, max_over_ranks,
+                                                  all_ranks_ok)
     except Exception as e:  # keep the headline line even if an extra leg fails
         extras["extras_error"] = f"{type(e).__name__}: {e}"
     if not args.no_config5:
@@ -553,7 +559,7 @@ def run_ours(args):
             import gc
             gc.collect()
             ctx.trim()
-            extras["config5_sycamore53_d12"] = config5_sycamore(tb, ctx, dist, rank, world, max_over_ranks)
+            extras["config5_sycamore53_d12"] = config5_sycamore(tb, ctx, dist, rank, world, max_over_ranks, all_ranks_ok)
         except Exception as e:
             extras["config5_error"] = f"{type(e).__name__}: {e}"
     if rank == 0:
@@ -584,7 +590,7 @@ CONFIG5_PATH = os.path.join("bench_inputs", "sycamore53_d12.json")
 CONFIG5_AMPLITUDE = complex(-6.148484459425177e-09, -5.130555022162778e-09)
 
 
-def config5_sycamore(tb, ctx, dist, rank, world, max_over_ranks, steps=2):
+def config5_sycamore(tb, ctx, dist, rank, world, max_over_ranks, all_ranks_ok, steps=2):
     """BASELINE config 5: Sycamore-53 depth-12 single amplitude as 2^s slices of one replace-left path (found offline by
     tools/search_path.py: random-greedy + subtree reconfiguration + slicing under the device-time model), slices round-robin
     over the ranks, one ncclAllReduce.  Timed: every slice through the compiled plan (leaves resident) + all-reduce + D2H of
@@ -599,7 +605,14 @@ def config5_sycamore(tb, ctx, dist, rank, world, max_over_ranks, steps=2):
     legs = d["sliced_legs"]
     flops_slice, peak, _ = path_cost([(t.legs, t.bond_dims) for t in tn5.tensors], path5, legs)
     t0 = time.perf_counter()
-    sp = SlicedPlan(tn5, path5, legs, ctx=ctx)
+    sp, err = None, None
+    try:
+        sp = SlicedPlan(tn5, path5, legs, ctx=ctx)
+    except Exception as e:      # e.g. no room for the 64 GiB workspace on ONE rank: every rank must skip the leg together
+        err = e
+    if not all_ranks_ok(err is None):
+        sp = None
+        raise RuntimeError(f"setup failed on a rank (this rank: {err!r})")
     setup = time.perf_counter() - t0
     ts, amp5 = [], None
     for it in range(1 + steps):
@@ -625,28 +638,34 @@ def config5_sycamore(tb, ctx, dist, rank, world, max_over_ranks, steps=2):
                             "profiles/r02_config5_sycamore53_d12.jsonl)"}
 
 
-def parity_and_modes(tb, ctx, dist, torch, stream, tn, fpath, net, path, amp_fanin, rank, world, local, meta_group, max_over_ranks):
+def parity_and_modes(tb, ctx, dist, torch, stream, tn, fpath, net, path, amp_fanin, rank, world, local, meta_group, max_over_ranks, all_ranks_ok):
     """Rank 0: flat 1-GPU amplitude of the same network (greedy path) and the partitioned path executed on ONE GPU;
     all ranks: the sliced mode (2^s slices round-robin + one ncclAllReduce).  Asserts |amp_N - amp_flat| <= 1e-9 |amp_flat|."""
     from tnc_b200.contractionpath.slicing import SlicedPlan, find_slices
     from tnc_b200.tensornetwork import contract_tensor_network
     out = {}
     flat = None
-    if rank == 0:
-        flat = complex(contract_tensor_network(tn, fpath, ctx=ctx).to_numpy())
-        ctx.synchronize()
-        ts = []
-        for _ in range(3):
-            t0 = time.perf_counter()
-            one = complex(contract_tensor_network(net, path, ctx=ctx).to_numpy())
-            ts.append(time.perf_counter() - t0)
-        out["same_partitioned_path_on_1gpu_ms"] = float(np.median(ts)) * 1e3
-        out["fanin"] = {"amplitude": [amp_fanin.real, amp_fanin.imag], "rel_diff_vs_flat": abs(amp_fanin - flat) / abs(flat),
-                        "rel_diff_vs_same_path_1gpu": abs(amp_fanin - one) / abs(one)}
-    legs = find_slices(tn, fpath, min_slices=max(8, world))
-    t0 = time.perf_counter()
-    sp = SlicedPlan(tn, fpath, legs, ctx=ctx)          # compile once + stage every slice's leaves (planning, untimed)
-    setup_ms = (time.perf_counter() - t0) * 1e3
+    err = None
+    try:
+        if rank == 0:
+            flat = complex(contract_tensor_network(tn, fpath, ctx=ctx).to_numpy())
+            ctx.synchronize()
+            ts = []
+            for _ in range(3):
+                t0 = time.perf_counter()
+                one = complex(contract_tensor_network(net, path, ctx=ctx).to_numpy())
+                ts.append(time.perf_counter() - t0)
+            out["same_partitioned_path_on_1gpu_ms"] = float(np.median(ts)) * 1e3
+            out["fanin"] = {"amplitude": [amp_fanin.real, amp_fanin.imag], "rel_diff_vs_flat": abs(amp_fanin - flat) / abs(flat),
+                            "rel_diff_vs_same_path_1gpu": abs(amp_fanin - one) / abs(one)}
+        legs = find_slices(tn, fpath, min_slices=max(8, world))
+        t0 = time.perf_counter()
+        sp = SlicedPlan(tn, fpath, legs, ctx=ctx)          # compile once + stage every slice's leaves (planning, untimed)
+        setup_ms = (time.perf_counter() - t0) * 1e3
+    except Exception as e:      # a failure on ONE rank (rank 0's reference legs, a plan that does not fit) ends the leg on ALL ranks
+        err = e
+    if not all_ranks_ok(err is None):
+        raise RuntimeError(f"parity leg failed on a rank before its collectives (this rank: {err!r})")
     ts = []
     for _ in range(4):
         dist.barrier(); ctx.synchronize()
