@@ -166,3 +166,65 @@ def test_python_circuit_matches_oracle_structure():
     assert perm.target_leg_order == ofinal == [4, 6, 7]
     with pytest.raises(ValueError, match="Qubit arguments must be unique"):
         c.append_gate("cx", [], [q[1], q[1]])
+
+
+def test_marshalled_tree_round_trips(built_lib):
+    """The C tree handed to tncb_contract_tensor_network (tncb_tn, include/tncb.h) read back field by field equals the
+    Python `Tensor` tree it was built from: gate / matrix / file / empty leaves, nested composites, angle packing."""
+    from tnc_b200.builders import random_circuit
+    from tnc_b200.tensornetwork import Tensor, TensorData
+    from tnc_b200.tensornetwork import contraction as ct
+
+    def read(addr, n, keep):
+        rec = np.frombuffer((C.c_char * (n * ct._TN_DTYPE.itemsize)).from_address(addr), dtype=ct._TN_DTYPE)
+        out = []
+        for r in rec:
+            rk = int(r["rank"])
+            d = {"legs": [int(x) for x in np.frombuffer((C.c_char * (8 * rk)).from_address(int(r["legs"])), dtype=np.uint64)] if rk else [],
+                 "dims": [int(x) for x in np.frombuffer((C.c_char * (8 * rk)).from_address(int(r["dims"])), dtype=np.uint64)] if rk else [],
+                 "kind": int(r["kind"])}
+            if d["kind"] == 2:
+                na = int(r["n_gate_angles"])
+                ang = tuple(np.frombuffer((C.c_char * (8 * na)).from_address(int(r["gate_angles"])), dtype=np.float64)) if na else ()
+                d["gate"] = (C.string_at(int(r["gate_name"])).decode(), ang, bool(r["gate_adjoint"]))
+            if d["kind"] == 1:
+                d["host"] = int(r["host_re_im"])
+            if d["kind"] == 4:
+                d["file"] = (C.string_at(int(r["file_path"])).decode(), bool(r["file_adjoint"]))
+            if r["n_children"]:
+                d["children"] = read(int(r["children"]), int(r["n_children"]), keep)
+            out.append(d)
+        return out
+
+    def expect(t, host_ptrs):
+        if t.tensors:
+            return {"legs": [], "dims": [], "kind": 0, "children": [expect(c, host_ptrs) for c in t.tensors]}
+        td = t.tensordata
+        d = {"legs": list(t.legs), "dims": list(t.bond_dims), "kind": {"uncontracted": 0, "matrix": 1, "gate": 2, "file": 4}[td.kind]}
+        if td.kind == "gate":
+            d["gate"] = (td.gate[0], tuple(td.gate[1]), td.gate[2])
+        if td.kind == "matrix":
+            d["host"] = host_ptrs[id(td.matrix)]
+        if td.kind == "file":
+            d["file"] = td.file
+        return d
+
+    rc = random_circuit(12, 8, 0.5, 0.5, np.random.default_rng(9))
+    n = len(rc.tensors)
+    a = np.arange(8, dtype=np.complex128).reshape(2, 4)
+    ta = Tensor.new([0, 1], [2, 4]); ta.set_tensor_data(TensorData.Matrix(a))
+    tf = Tensor.new([1, 2], [4, 3]); tf.set_tensor_data(TensorData.File("/tmp/some file.h5", True))
+    nested = Tensor.new_composite([Tensor.new_composite(rc.tensors[:n // 3]), Tensor.new_composite(rc.tensors[n // 3:]),
+                                   Tensor.new_composite([ta, tf, Tensor.new([], [])])])
+    for tn in (rc, nested):
+        m = ct._Marshal()
+        c_tn = m.tn(tn)
+        got = read(C.addressof(c_tn), 1, m.keep)[0]
+        host_ptrs = {}
+        def walk(t):
+            for c in t.tensors:
+                walk(c)
+            if not t.tensors and t.tensordata.kind == "matrix":
+                host_ptrs[id(t.tensordata.matrix)] = np.asarray(t.tensordata.matrix).__array_interface__["data"][0]
+        walk(tn)
+        assert got == expect(tn, host_ptrs)

@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+from itertools import chain
 from typing import List, Optional
 
 import numpy as np
@@ -31,10 +32,11 @@ _GATE_NAMES = {}
 
 
 def _gate_name_ptr(name: str) -> int:
-    buf = _GATE_NAMES.get(name)
-    if buf is None:
-        buf = _GATE_NAMES[name] = C.create_string_buffer(name.encode())     # interned: stays alive for the process
-    return C.addressof(buf)
+    hit = _GATE_NAMES.get(name)
+    if hit is None:
+        buf = C.create_string_buffer(name.encode())                         # interned: stays alive for the process
+        hit = _GATE_NAMES[name] = (C.addressof(buf), buf)
+    return hit[0]
 
 
 class _Marshal:
@@ -51,61 +53,74 @@ class _Marshal:
         self.keep.append(rec)
         ranks = [len(t.legs) for t in tensors]
         tot = sum(ranks)
-        legs = np.fromiter((l for t in tensors for l in t.legs), dtype=np.uint64, count=tot)
-        dims = np.fromiter((d for t in tensors for d in t.bond_dims), dtype=np.uint64, count=tot)
+        legs = np.fromiter(chain.from_iterable(t.legs for t in tensors), dtype=np.uint64, count=tot)
+        dims = np.fromiter(chain.from_iterable(t.bond_dims for t in tensors), dtype=np.uint64, count=tot)
         self.keep += [legs, dims]
         off = np.zeros(n, dtype=np.uint64)
         if n > 1:
             np.cumsum(np.asarray(ranks[:-1], dtype=np.uint64), out=off[1:])
-        rec["rank"] = ranks
         rec["legs"] = legs.ctypes.data + 8 * off
         rec["dims"] = dims.ctypes.data + 8 * off
-        n_ang = sum(len(t.tensordata.gate[1]) for t in tensors if t.tensordata.kind == "gate")
-        angles = np.zeros(max(n_ang, 1), dtype=np.float64)
-        self.keep.append(angles)
-        apos = 0
+        # one pass over the leaves into plain lists, one column assignment per field (a numpy record setitem or an
+        # ndarray.ctypes access per leaf costs more than everything else in this function)
+        kind, n_children, children = [0] * n, [0] * n, [0] * n
+        host, device, gate_name, gate_adj, gate_ang, n_ang = [0] * n, [0] * n, [0] * n, [0] * n, [0] * n, [0] * n
+        file_path, file_adj = [0] * n, [0] * n
+        ang_vals: List[float] = []
         for i, t in enumerate(tensors):
             if t.tensors:
-                rec[i]["n_children"] = len(t.tensors)
-                rec[i]["children"] = self._children(t.tensors)
-                rec[i]["rank"] = 0
+                n_children[i] = len(t.tensors)
+                children[i] = self._children(t.tensors)
+                ranks[i] = 0
                 continue
             td = t.tensordata
             k = td.kind
             if k == "gate":
                 name, ang, adj = td.gate
-                r = rec[i]
-                r["kind"] = 2
-                r["gate_name"] = _gate_name_ptr(name)
-                r["gate_adjoint"] = int(adj)
+                kind[i] = 2
+                gate_name[i] = _gate_name_ptr(name)
+                gate_adj[i] = int(adj)
+                gate_ang[i] = 8 * len(ang_vals)        # byte offset into `angles`, made absolute below
                 if ang:
-                    angles[apos:apos + len(ang)] = ang
-                    r["gate_angles"] = angles.ctypes.data + 8 * apos
-                    r["n_gate_angles"] = len(ang)
-                    apos += len(ang)
-                else:
-                    r["gate_angles"] = angles.ctypes.data
+                    n_ang[i] = len(ang)
+                    ang_vals.extend(ang)
             elif k == "matrix":
                 m = td.matrix
                 if isinstance(m, DeviceTensor):
                     if m.handle is None:   # consumed by an earlier call (the Rust move left TensorData::Uncontracted behind)
                         raise TncbError(-3, "Cannot convert uncontracted tensor to data (device tensor already consumed)")
-                    rec[i]["kind"] = 3
-                    rec[i]["device"] = m.handle.value or 0
+                    kind[i] = 3
+                    device[i] = m.handle.value or 0
                     self.device_inputs.append(m)
                 else:
                     arr = np.asarray(m, dtype=np.complex128, order="C")
                     if list(arr.shape) != list(t.bond_dims):
                         arr = arr.reshape(t.bond_dims)
                     self.keep.append(arr)
-                    rec[i]["kind"] = 1
-                    rec[i]["host_re_im"] = arr.ctypes.data
+                    kind[i] = 1
+                    host[i] = arr.__array_interface__["data"][0]
             elif k == "file":   # TensorData::File((path, adjoint)): loaded by the library while it stages the leaves
                 buf = C.create_string_buffer(os.fsencode(td.file[0]))
                 self.keep.append(buf)
-                rec[i]["kind"] = 4
-                rec[i]["file_path"] = C.addressof(buf)
-                rec[i]["file_adjoint"] = int(bool(td.file[1]))
+                kind[i] = 4
+                file_path[i] = C.addressof(buf)
+                file_adj[i] = int(bool(td.file[1]))
+        angles = np.zeros(max(len(ang_vals), 1), dtype=np.float64)
+        angles[:len(ang_vals)] = ang_vals
+        self.keep.append(angles)
+        abase = angles.__array_interface__["data"][0]
+        rec["rank"] = ranks
+        rec["kind"] = kind
+        rec["n_children"] = n_children
+        rec["children"] = children
+        rec["host_re_im"] = host
+        rec["device"] = device
+        rec["gate_name"] = gate_name
+        rec["gate_adjoint"] = gate_adj
+        rec["n_gate_angles"] = n_ang
+        rec["gate_angles"] = [abase + o if kd == 2 else 0 for o, kd in zip(gate_ang, kind)]
+        rec["file_path"] = file_path
+        rec["file_adjoint"] = file_adj
         return rec.ctypes.data
 
     def tn(self, t: Tensor) -> TncbTn:
