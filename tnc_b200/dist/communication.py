@@ -83,19 +83,23 @@ def contracted_legs(tn: Tensor, path: ContractionPath) -> Tuple[List[int], List[
     serialised tensor carries its legs (serialization.rs:43-67); here only raw data travels."""
     if tn.is_leaf():
         return list(tn.legs), list(tn.bond_dims)
-    ts: List[Optional[Tensor]] = []
+    # plain (legs, dims) lists instead of Tensor objects: this runs on rank 0 inside the timed scatter for every partition
+    ts: List[Optional[Tuple[List[int], List[int]]]] = []
     for i, c in enumerate(tn.tensors):
         if c.is_composite() and i in path.nested:
-            l, d = contracted_legs(c, path.nested[i])
-            ts.append(Tensor(l, d))
+            ts.append(contracted_legs(c, path.nested[i]))
         else:
-            ts.append(Tensor(c.legs, c.bond_dims) if c.is_leaf() else None)
+            ts.append((c.legs, c.bond_dims) if c.is_leaf() else None)
     for (i, j) in path.toplevel:
-        ts[i] = ts[j] ^ ts[i]
+        (al, ad), (bl, bd) = ts[i], ts[j]
+        sa, sb = set(al), set(bl)
+        keep_b = [q for q, l in enumerate(bl) if l not in sa]       # tensor.rs:463-479: (b \ a) ++ (a \ b), order-preserving
+        keep_a = [q for q, l in enumerate(al) if l not in sb]
+        ts[i] = ([bl[q] for q in keep_b] + [al[q] for q in keep_a], [bd[q] for q in keep_b] + [ad[q] for q in keep_a])
         ts[j] = None
     rest = [t for t in ts if t is not None]
     assert len(rest) == 1, "Not fully contracted"
-    return list(rest[0].legs), list(rest[0].bond_dims)
+    return list(rest[0][0]), list(rest[0][1])
 
 
 def fanin_schedule(comm: Communication, toplevel) -> List[dict]:
