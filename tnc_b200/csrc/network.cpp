@@ -316,6 +316,8 @@ struct tncb_plan {
   tncb_ctx* ctx = nullptr;           // device state is tied to this context (stream, device)
   void* ws = nullptr;                // arena block
   void* stage = nullptr;             // plan-owned pinned staging of the leaf block
+  cudaEvent_t stage_ev = nullptr;    // recorded after the last eager upload out of `stage` (re-staging waits for it)
+  bool stage_busy = false;
   bool leaves_resident = false;      // tncb_plan_stage put the leaf block into ws
   cudaGraphExec_t exec[2] = {nullptr, nullptr};    // [0]: with the H2D of the staged leaves, [1]: leaves resident
   uint64_t kernels_per_run = 0;
@@ -511,7 +513,9 @@ static int execute_static(tncb_ctx* ctx, tncb_plan* P, const tncb_tn* tn, tncb_t
   char* ws = (char*)P->ws;
   const int which = tn ? 0 : 1;
   if (tn) {
-    if (P->exec[0] || P->leaves_resident) TNCB_CUDA(cudaStreamSynchronize(ctx->stream));   // an earlier copy may still read the staging buffer
+    // an earlier upload may still read the staging buffer (it waits behind the previous network's kernels on the stream)
+    if (P->exec[0] || P->leaves_resident) TNCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    else if (P->stage_busy) TNCB_CUDA(cudaEventSynchronize(P->stage_ev));
     if ((rc = stage_leaves(S, leaves, (std::complex<double>*)P->stage))) return rc;
     P->leaves_resident = false;     // the workspace copy is about to be overwritten with this call's payloads
   }
@@ -540,7 +544,12 @@ static int execute_static(tncb_ctx* ctx, tncb_plan* P, const tncb_tn* tn, tncb_t
     ctx->launches += P->kernels_per_run;
     ctx->engine_count[0] += S.steps.size();   // (graphable plans hold K0 / K2 pairs only; counted as tiny pairs)
   } else {
-    if (tn) TNCB_CUDA(cudaMemcpyAsync(ws + P->leaf_off, P->stage, block_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (tn) {
+      TNCB_CUDA(cudaMemcpyAsync(ws + P->leaf_off, P->stage, block_bytes, cudaMemcpyHostToDevice, ctx->stream));
+      if (!P->stage_ev) TNCB_CUDA(cudaEventCreateWithFlags(&P->stage_ev, cudaEventDisableTiming));
+      TNCB_CUDA(cudaEventRecord(P->stage_ev, ctx->stream));
+      P->stage_busy = true;
+    }
     if ((rc = enqueue_static(ctx, P))) return rc;
   }
   tncb_tensor* result = nullptr;
@@ -805,6 +814,7 @@ void tncb_plan_release_device_state(tncb_plan* plan) {
   plan->leaves_resident = false;
   if (plan->ws) { ctx->arena.free(plan->ws, plan->ws_bytes); plan->ws = nullptr; }
   if (plan->stage) { cudaFreeHost(plan->stage); plan->stage = nullptr; }
+  if (plan->stage_ev) { cudaEventDestroy(plan->stage_ev); plan->stage_ev = nullptr; plan->stage_busy = false; }
   if (plan->resident) { ctx->arena.free(plan->resident, plan->resident_bytes); plan->resident = nullptr; }
   for (size_t i = 0; i < ctx->plans.size(); i++)
     if (ctx->plans[i] == plan) { ctx->plans.erase(ctx->plans.begin() + i); break; }
