@@ -1,4 +1,5 @@
-"""TensorData::File leaves through contract_tensor_network on the device (tensordata.rs:43-49 inside contraction.rs:66-76):
+"""(Named to sort after the other GPU files: the driver runs `pytest -x`.)
+TensorData::File leaves through contract_tensor_network on the device (tensordata.rs:43-49 inside contraction.rs:66-76):
 the library loads the HDF5 payloads while it stages the leaves, so a network whose gates come from files must give the same
 amplitude as the same network with in-memory payloads -- bit for bit, because the schedule and the staged bytes are equal."""
 import numpy as np
@@ -99,3 +100,49 @@ def test_file_leaf_errors_leave_the_call_clean(ctx, tmp_path):
     # the context is still usable after the failures
     got = contract_tensor_network(Tensor.new_composite([ta, tb]), path, ctx=ctx)
     np.testing.assert_allclose(got.to_numpy(), np.einsum("ik,kj->ji", a, b), rtol=0, atol=1e-14)
+
+
+def test_cpp_file_leaf(built_lib, tmp_path):
+    """the same through the C++ mirror (tnc::TensorData::file, include/tnc.hpp)"""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([os.path.join(root, "build", "test_host_api"), "--file-leaf", str(tmp_path)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    assert r.returncode == 0 and "HOST_FILE_LEAF_OK" in r.stdout, r.stdout
+
+
+def test_back_to_back_cached_calls_keep_their_own_payloads(built_lib):
+    """Three contract_tensor_network calls with DIFFERENT payloads of one structure, issued without any synchronisation
+    while the stream is still busy: each call's leaf upload must read its own payloads (the cached plan re-uses one
+    pinned staging buffer; re-staging waits for the previous upload)."""
+    import tnc_b200 as tb
+    from tnc_b200.contractionpath import ContractionPath
+    from tnc_b200.tensornetwork import Tensor, TensorData, contract_tensor_network
+    c = tb.Context(0)
+    try:
+        rng = np.random.default_rng(4)
+
+        def rnd(*s):
+            return rng.uniform(-1, 1, s) + 1j * rng.uniform(-1, 1, s)
+
+        def net(a, b, v):
+            ta = Tensor.new([0, 1], [64, 64]); ta.set_tensor_data(TensorData.Matrix(a))
+            tb_ = Tensor.new([1, 2], [64, 64]); tb_.set_tensor_data(TensorData.Matrix(b))
+            tv = Tensor.new([2], [64]); tv.set_tensor_data(TensorData.Matrix(v))
+            return Tensor.new_composite([ta, tb_, tv])
+
+        path = ContractionPath.simple([(0, 1), (0, 2)])       # (a b) v: a 64^3 pair (K1, so no CUDA graph) and a matrix-vector pair
+        data = [(rnd(64, 64), rnd(64, 64), rnd(64)) for _ in range(4)]
+        for _ in range(2):                                     # first sighting runs pair by pair, the second compiles the plan
+            contract_tensor_network(net(*data[0]), path, ctx=c).to_numpy()
+        big = [tb.DeviceTensor.from_numpy(c, rnd(2048, 2048)) for _ in range(3)]
+        for _ in range(4):                                     # a few ms of queued work: the uploads below wait behind it
+            tb.contract_pair_into(c, [0, 1], big[0], [1, 2], big[1], big[2])
+        nets = [net(*d) for d in data[1:]]
+        res = [contract_tensor_network(n, path, ctx=c) for n in nets]
+        for r, (a, b, v) in zip(res, data[1:]):
+            assert r.legs == [0]
+            exp = a @ b @ v
+            assert np.abs(r.to_numpy() - exp).max() <= 1e-12 * np.abs(exp).max()
+    finally:
+        c.close()
