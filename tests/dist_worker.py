@@ -39,6 +39,17 @@ def cpu_logic(rank, world, port, q):
         tn, fpath, ptn, ppath = build_case(parts=world) if rank == 0 else (None, None, None, None)
         local_tn, local_path, comm = scatter_tensor_network(ptn, ppath, rank, world)
         toplevel = broadcast_path(ppath.toplevel if rank == 0 else None, 0)
+        # over a gloo group the fan-in path rides along with the scatter (one collective): same content
+        assert [tuple(x) for x in comm.toplevel] == [tuple(x) for x in toplevel]
+        from tnc_b200.dist.communication import _scatter_with_toplevel
+        top2, tn2, path2, comm2 = _scatter_with_toplevel(ptn, ppath, rank, world, None)
+        assert [tuple(x) for x in top2] == [tuple(x) for x in toplevel] and comm2 == comm and path2 == local_path
+        assert [(t.legs, t.bond_dims, t.tensordata.kind, t.tensordata.gate) for t in tn2.tensors] == \
+               [(t.legs, t.bond_dims, t.tensordata.kind, t.tensordata.gate) for t in local_tn.tensors]
+        if rank == 0:   # the scattered partition is the partition rank 0 holds
+            orig = ptn.tensor(comm.tensor(0))
+            assert [(t.legs, t.bond_dims, t.tensordata.kind, t.tensordata.gate) for t in orig.tensors] == \
+                   [(t.legs, t.bond_dims, t.tensordata.kind, t.tensordata.gate) for t in local_tn.tensors]
         mine = comm.tensor(rank)
         assert mine is not None and local_tn.is_composite()
         assert len(local_path.toplevel) == len(local_tn.tensors) - 1

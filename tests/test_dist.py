@@ -36,6 +36,31 @@ def test_gloo_host_logic(built_lib, world):
     assert sorted(r for _, r in res[0][0]) == list(range(world))
 
 
+def test_partition_packing_round_trips(built_lib):
+    """the compact form partitions travel in (dist.communication._pack_tensor) loses nothing: nested composites, gate,
+    matrix, file and empty leaves"""
+    import pickle
+    import numpy as np
+    from tnc_b200.builders import random_circuit
+    from tnc_b200.dist.communication import _pack_tensor, _unpack_tensor
+    from tnc_b200.tensornetwork import Tensor, TensorData
+    rc = random_circuit(8, 5, 0.5, 0.5, np.random.default_rng(2))
+    m = Tensor.new([0, 1], [2, 4]); m.set_tensor_data(TensorData.Matrix(np.arange(8, dtype=np.complex128).reshape(2, 4)))
+    f = Tensor.new([1, 2], [4, 3]); f.set_tensor_data(TensorData.File("x.h5", True))
+    tn = Tensor.new_composite([Tensor.new_composite(rc.tensors[:7]), Tensor.new_composite(rc.tensors[7:]), Tensor.new_composite([m, f, Tensor.new([], [])])])
+
+    def same(a, b):
+        assert a.legs == b.legs and a.bond_dims == b.bond_dims and len(a.tensors) == len(b.tensors)
+        ta, tb = a.tensordata, b.tensordata
+        assert ta.kind == tb.kind and ta.gate == tb.gate and ta.file == tb.file
+        if ta.kind == "matrix":
+            np.testing.assert_array_equal(ta.matrix, tb.matrix)
+        for x, y in zip(a.tensors, b.tensors):
+            same(x, y)
+
+    same(tn, _unpack_tensor(pickle.loads(pickle.dumps(_pack_tensor(tn), protocol=pickle.HIGHEST_PROTOCOL))))
+
+
 @pytest.mark.gpu
 def test_nccl_fanin_equals_flat():
     import torch
