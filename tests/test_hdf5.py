@@ -193,6 +193,25 @@ def test_reader_handles_newer_encodings(h5, tmp_path, userblock):
     assert h5.load_data(p).size == 0                                   # first member is "-1": null dataspace, no data
 
 
+def test_foreign_attributes_are_skipped(h5, tmp_path):
+    """an attribute of a type outside the subset (here a variable-length string, as h5py writes for str attributes) next
+    to `bids` does not make the dataset unreadable"""
+    F = h5check.LatestFile()
+    a = (np.arange(6) + 1j).reshape(2, 3)
+    vlen = bytes([0x19, 0x01, 0, 0]) + struct.pack("<I", 16) + bytes([0x13, 0, 0, 0]) + struct.pack("<I", 1)
+    nm, sp = b"note\0", h5check._space_v2([])
+    attr = bytes([3, 0]) + struct.pack("<HHH", len(nm), len(vlen), len(sp)) + b"\0" + nm + vlen + sp + b"\0" * 16
+    ds = F.dataset(a.shape, h5check._complex_type_v3(), F.contiguous(a.tobytes()), attrs=[attr, h5check._attr_v3("bids", [3, 4], 8, False)])
+    p = tmp_path / "vlen.h5"
+    p.write_bytes(F.finish(F.group([("tensors", F.group([("0", ds)]))])))
+    with h5.Hdf5File(p) as f:
+        assert f.member_names() == ["0"] and f.attr(0, "bids") == [3, 4]
+        np.testing.assert_array_equal(f.read(0), a)
+        from tnc_b200 import TncbError
+        with pytest.raises(TncbError):
+            f.attr(0, "note")                       # skipped, hence absent
+
+
 def test_unsupported_features_are_named(h5, tmp_path):
     """dense link storage (fractal heap address defined) -> TNCB_ERR_UNSUPPORTED, not a wrong answer"""
     from tnc_b200 import TncbError

@@ -426,7 +426,10 @@ static Dataset read_dataset(const File& f, const std::string& name, uint64_t hea
       }
       case 0x08: read_layout(f, m, d); break;
       case 0x0b: read_filters(m, d.filters); break;
-      case 0x0c: d.attrs.push_back(read_attribute(f, m)); break;
+      case 0x0c:                              // an attribute of a type outside the subset (strings of other producers,
+        try { d.attrs.push_back(read_attribute(f, m)); }      // references, enums ...) is skipped, not fatal: only the
+        catch (const IoError& e) { if (e.code != TNCB_ERR_UNSUPPORTED) throw; }   // integer arrays `bids` / `tids` are read
+        break;
       case 0x15: {                            // attribute info: dense storage when the fractal heap exists
         Cur c{m.data, m.data + m.size};
         c.skip(1); int flags = c.u8();
