@@ -146,3 +146,26 @@ def test_back_to_back_cached_calls_keep_their_own_payloads(built_lib):
             assert np.abs(r.to_numpy() - exp).max() <= 1e-12 * np.abs(exp).max()
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("qubits,rounds,locations,seed", [(8, 4, [3], 1), (10, 5, [2, 7], 2), (12, 4, [0, 5, 11], 3)])
+def test_observable_circuit_vs_oracle(ctx, qubits, rounds, locations, seed):
+    """random_circuit_with_set_observable (random_circuit.rs:120-276): the light-cone expectation-value network contracts to
+    the oracle's value (possibly several disconnected components -> outer products of scalars)."""
+    from tnc_b200.builders import random_circuit_with_set_observable
+    from tnc_b200.tensornetwork import contract_tensor_network
+    tn = random_circuit_with_set_observable(qubits, rounds, 0.7, 0.7, locations, np.random.default_rng(seed), "line", qubits)
+    path = _greedy(tn)
+
+    def to_o(t):
+        if t.is_composite():
+            return orc.OTensor(children=[to_o(c) for c in t.tensors])
+        td = t.tensordata
+        d = ("gate", td.gate[0], td.gate[1], td.gate[2]) if td.kind == "gate" else np.asarray(td.matrix)
+        return orc.OTensor(list(t.legs), list(t.bond_dims), d)
+
+    res = contract_tensor_network(tn, path, ctx=ctx)
+    ref = orc.contract_tensor_network(to_o(tn), orc.OPath(list(path.toplevel), {}))
+    assert res.legs == ref.legs == []
+    got, exp = complex(res.to_numpy()), complex(ref.data)
+    assert abs(got - exp) <= 1e-9 * abs(exp) + 1e-15, (got, exp)

@@ -19,6 +19,14 @@ class Permutor:
     def is_identity(self) -> bool:
         return not self.target_leg_order
 
+    @staticmethod
+    def permutation_between(given: Sequence[int], target: Sequence[int]) -> List[int]:
+        """circuit_builder.rs:125-129: the permutation p with [given[p[i]] for i] == target (`given` and `target` are equal
+        up to order) -- the axis order handed to tncb_permute."""
+        pos = {l: i for i, l in enumerate(given)}
+        assert len(pos) == len(given) == len(target) and set(pos) == set(target), "given and target must be permutations of each other"
+        return [pos[l] for l in target]
+
     def apply(self, tensor: Tensor, ctx: Optional[Context] = None) -> Tensor:
         """Transposes the (device) data so that the legs appear in the target order
         (circuit_builder.rs:86-114); one tncb_permute launch."""
@@ -26,7 +34,7 @@ class Permutor:
         if self.is_identity():
             return tensor
         ctx = ctx or default_context()
-        perm = [tensor.legs.index(l) for l in self.target_leg_order]
+        perm = self.permutation_between(tensor.legs, self.target_leg_order)
         m = tensor.tensordata.matrix
         dt = m if isinstance(m, DeviceTensor) else DeviceTensor.from_numpy(ctx, np.asarray(m).reshape(tensor.bond_dims))
         out = C.c_void_p()

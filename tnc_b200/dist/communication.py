@@ -60,6 +60,46 @@ def get_tensor_mapping(path: ContractionPath, size: int) -> Dict[int, int]:
     return {p: int(ranks[i]) for i, p in enumerate(parts)}
 
 
+class RankTensorMapping:
+    """mpi/mpi_types.rs:6-62: a bidirectional (1:1) mapping between ranks and composite tensors; every tensor maps to a rank,
+    not every rank to a tensor."""
+
+    def __init__(self):
+        self._pairs: List[Tuple[int, int]] = []
+
+    @classmethod
+    def from_dict(cls, tensor_to_rank: Dict[int, int]) -> "RankTensorMapping":
+        m = cls()
+        for t, r in tensor_to_rank.items():
+            m.insert(r, t)
+        return m
+
+    def insert(self, rank: int, tensor: int) -> None:
+        assert self.tensor(rank) is None, f"Rank {rank} is already associated with a tensor"
+        assert self._rank_opt(tensor) is None, f"Tensor {tensor} is already associated with a rank"
+        self._pairs.append((int(rank), int(tensor)))
+
+    def _rank_opt(self, tensor: int) -> Optional[int]:
+        return next((r for r, t in self._pairs if t == tensor), None)
+
+    def rank(self, tensor: int) -> int:
+        r = self._rank_opt(tensor)
+        assert r is not None, f"Tensor {tensor} has no rank"
+        return r
+
+    def tensor(self, rank: int) -> Optional[int]:
+        return next((t for r, t in self._pairs if r == rank), None)
+
+    def __len__(self) -> int:
+        return len(self._pairs)
+
+    def is_empty(self) -> bool:
+        return not self._pairs
+
+    def __iter__(self):
+        return iter(self._pairs)
+
+
 @dataclass
 class Communication:
     """Opaque in the reference (communication.rs:118-120); also carries the external legs of
