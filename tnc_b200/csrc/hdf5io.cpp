@@ -119,6 +119,8 @@ struct File {
   uint64_t base = 0;
   int O = 8, L = 8;
   uint64_t root_header = UNDEF;
+  mutable uint64_t nodes_visited = 0;      // B-tree nodes walked so far: a cyclic (corrupted) tree must end in an error, not in a loop
+  void visit_node() const { if (++nodes_visited > (1u << 22)) bad("B-tree with more than 2^22 nodes (cyclic?)"); }
   std::vector<Dataset> tensors;            // members of the opened group, ascending by name (H5_INDEX_NAME, H5_ITER_INC)
 
   ~File() {
@@ -450,6 +452,7 @@ struct Link { std::string name; uint64_t header; };
 
 static void walk_group_btree(const File& f, uint64_t node, const uint8_t* heap, size_t heap_size, std::vector<Link>& out, int depth) {
   if (depth > 16) bad("group B-tree deeper than 16 levels");
+  f.visit_node();
   Cur c = f.cur_to_end(node);
   if (std::memcmp(c.take(4), "TREE", 4) != 0) bad("group B-tree node without its signature");
   if (c.u8() != 0) bad("group B-tree node of the wrong type");
@@ -583,6 +586,7 @@ static void unshuffle(std::vector<uint8_t>& buf, size_t esize) {
 
 static void read_chunks(const File& f, const Dataset& d, const ElemKind& k, uint64_t node, double* out, int depth) {
   if (depth > 16) bad("chunk B-tree deeper than 16 levels");
+  f.visit_node();
   const size_t rank = d.dims.size();
   const uint32_t esize = d.type.size;
   Cur c = f.cur_to_end(node);
