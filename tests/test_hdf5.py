@@ -225,6 +225,22 @@ def test_unsupported_features_are_named(h5, tmp_path):
     assert e.value.status == -9 and "dense link storage" in str(e.value)
 
 
+def test_cyclic_btree_is_an_error(h5, tmp_path):
+    """a B-tree child pointer bent back to its parent (300 members: a two-level tree) is reported, not followed forever"""
+    from tnc_b200 import TncbError
+    p = tmp_path / "cyc.h5"
+    h5.store_tensor(p, [(str(i), [i], np.zeros(1)) for i in range(300)], [])
+    raw = bytearray(p.read_bytes())
+    roots = [i for i in range(0, len(raw) - 8, 8) if raw[i:i + 4] == b"TREE" and raw[i + 4] == 0 and raw[i + 5] == 1]
+    assert len(roots) == 1                                           # the level-1 root of /tensors
+    r = roots[0]
+    raw[r + 24 + 8:r + 24 + 16] = struct.pack("<Q", r)               # child 0 := the root itself
+    p.write_bytes(bytes(raw))
+    with pytest.raises(TncbError) as e:
+        h5.Hdf5File(p)
+    assert e.value.status == -10 and "B-tree" in str(e.value)
+
+
 def test_not_hdf5_and_missing(h5, tmp_path):
     from tnc_b200 import TncbError
     p = tmp_path / "junk.h5"

@@ -450,20 +450,22 @@ static Dataset read_dataset(const File& f, const std::string& name, uint64_t hea
 // ---- groups -----------------------------------------------------------------------------------------
 struct Link { std::string name; uint64_t header; };
 
-static void walk_group_btree(const File& f, uint64_t node, const uint8_t* heap, size_t heap_size, std::vector<Link>& out, int depth) {
+static void walk_group_btree(const File& f, uint64_t node, const uint8_t* heap, size_t heap_size, std::vector<Link>& out, int depth,
+                             int expect_level = -1) {
   if (depth > 16) bad("group B-tree deeper than 16 levels");
   f.visit_node();
   Cur c = f.cur_to_end(node);
   if (std::memcmp(c.take(4), "TREE", 4) != 0) bad("group B-tree node without its signature");
   if (c.u8() != 0) bad("group B-tree node of the wrong type");
   int level = c.u8();
+  if (expect_level >= 0 && level != expect_level) bad("group B-tree: a child is not one level below its parent");
   size_t used = c.u16();
   c.skip(2 * (size_t)f.O);
   if (used > 65535 / 2) bad("group B-tree: too many entries");
   for (size_t i = 0; i < used; i++) {
     c.skip((size_t)f.L);                      // key i
     uint64_t child = read_addr(f, c);
-    if (level > 0) { walk_group_btree(f, child, heap, heap_size, out, depth + 1); continue; }
+    if (level > 0) { walk_group_btree(f, child, heap, heap_size, out, depth + 1, level - 1); continue; }
     Cur s = f.cur_to_end(child);
     if (std::memcmp(s.take(4), "SNOD", 4) != 0) bad("symbol table node without its signature");
     s.skip(2);
@@ -584,7 +586,7 @@ static void unshuffle(std::vector<uint8_t>& buf, size_t esize) {
   buf.swap(out);
 }
 
-static void read_chunks(const File& f, const Dataset& d, const ElemKind& k, uint64_t node, double* out, int depth) {
+static void read_chunks(const File& f, const Dataset& d, const ElemKind& k, uint64_t node, double* out, int depth, int expect_level = -1) {
   if (depth > 16) bad("chunk B-tree deeper than 16 levels");
   f.visit_node();
   const size_t rank = d.dims.size();
@@ -593,6 +595,7 @@ static void read_chunks(const File& f, const Dataset& d, const ElemKind& k, uint
   if (std::memcmp(c.take(4), "TREE", 4) != 0) bad("chunk B-tree node without its signature");
   if (c.u8() != 1) bad("chunk B-tree node of the wrong type");
   int level = c.u8();
+  if (expect_level >= 0 && level != expect_level) bad("chunk B-tree: a child is not one level below its parent");
   size_t used = c.u16();
   c.skip(2 * (size_t)f.O);
   uint64_t chunk_elems = 1;
@@ -606,7 +609,7 @@ static void read_chunks(const File& f, const Dataset& d, const ElemKind& k, uint
     std::vector<uint64_t> off(rank + 1);
     for (size_t q = 0; q <= rank; q++) off[q] = c.u64();
     uint64_t child = read_addr(f, c);
-    if (level > 0) { read_chunks(f, d, k, child, out, depth + 1); continue; }
+    if (level > 0) { read_chunks(f, d, k, child, out, depth + 1, level - 1); continue; }
     const uint8_t* raw = f.at(child, nbytes);
     std::vector<uint8_t> buf;
     const uint8_t* data = raw;
