@@ -283,13 +283,15 @@ def _recv(ctx: Context, legs, dims, peer: int) -> Tensor:
     return t
 
 
-def intermediate_reduce_tensor_network(local_tn: Tensor, toplevel, rank: int, comm: Communication, ctx: Context) -> Tensor:
+def intermediate_reduce_tensor_network(local_tn: Tensor, toplevel, rank: int, comm: Communication, ctx: Context, events=None) -> Tensor:
     """communication.rs:199-249: path-driven fan-in.  `local_tn` is this rank's contracted
     partition (a leaf with device data, or an empty Tensor).  Returns the local tensor after the
-    fan-in; on rank 0 that is the final result."""
+    fan-in; on rank 0 that is the final result.  `events`: a precomputed fanin_schedule(comm, toplevel)."""
     from ..tensornetwork.contraction import contract_tensor_network
     final_rank = 0
-    for ev in fanin_schedule(comm, toplevel):
+    if events is None:
+        events = fanin_schedule(comm, toplevel)
+    for ev in events:
         receiver, sender = ev["receiver"], ev["sender"]
         final_rank = receiver
         if receiver == rank:
@@ -305,8 +307,7 @@ def intermediate_reduce_tensor_network(local_tn: Tensor, toplevel, rank: int, co
             _send(ctx, local_tn, 0)
         if rank == 0:
             # the final tensor's legs are the last event's output
-            evs = fanin_schedule(comm, toplevel)
-            local_tn = _recv(ctx, evs[-1]["out_legs"], evs[-1]["out_dims"], final_rank)
+            local_tn = _recv(ctx, events[-1]["out_legs"], events[-1]["out_dims"], final_rank)
     return local_tn
 
 
@@ -342,9 +343,10 @@ class PartitionedPlan:
             self.plan = NetworkPlan(local_tn, local_path, ctx=ctx)
             self.plan.stage(local_tn)
         self.pairs_local = len(local_path.toplevel) if local_tn.is_composite() else 0
+        self.events = fanin_schedule(self.comm, self.toplevel)      # metadata only: derived once, identical on every rank
 
     def run(self) -> Tensor:
         local = self.plan.run() if self.plan is not None else Tensor()
         if self.plan is not None:
             assert local.legs == self.comm.external[self.mine][0], "fan-in metadata out of sync with the device result"
-        return intermediate_reduce_tensor_network(local, self.toplevel, self.rank, self.comm, self.ctx)
+        return intermediate_reduce_tensor_network(local, self.toplevel, self.rank, self.comm, self.ctx, self.events)
