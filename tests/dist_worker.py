@@ -67,6 +67,80 @@ def cpu_logic(rank, world, port, q):
         dist.destroy_process_group()
 
 
+def cpu_fanin(rank, world, port, q):
+    """gloo, no GPU: the WHOLE partitioned path of tnc_b200.dist (scatter, local contraction, path-driven fan-in, final hop;
+    contract_partitioned and PartitionedPlan) with the device engine swapped for the oracle and NCCL p2p for gloo
+    send / recv of host buffers.  What is under test is the host logic the GPU run depends on: which rank holds what, who
+    sends to whom in which order, the leg order a receiver assumes for a raw buffer, `[local, received]` as pair (0, 1)."""
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import tnc_oracle as orc
+        import tnc_b200.dist.communication as comm_mod
+        import tnc_b200.tensornetwork.contraction as con_mod
+        from tnc_b200.tensornetwork import Tensor, TensorData
+
+        def to_o(t):
+            if t.is_composite():
+                return orc.OTensor(children=[to_o(c) for c in t.tensors])
+            td = t.tensordata
+            d = ("gate", td.gate[0], td.gate[1], td.gate[2]) if td.kind == "gate" else (None if td.kind == "uncontracted" else np.asarray(td.matrix))
+            return orc.OTensor(list(t.legs), list(t.bond_dims), d)
+
+        def to_op(p):
+            return orc.OPath(list(p.toplevel), {i: to_op(x) for i, x in p.nested.items()})
+
+        def fake_contract(tn, path, ctx=None):
+            r = orc.contract_tensor_network(to_o(tn), to_op(path))
+            out = Tensor(r.legs, r.dims)
+            out.set_tensor_data(TensorData.Matrix(np.ascontiguousarray(r.data).reshape(r.dims)))
+            return out
+
+        def fake_send(ctx, t, peer):
+            buf = np.ascontiguousarray(np.asarray(t.tensordata.matrix, dtype=np.complex128)).reshape(-1)
+            dist.send(torch.from_numpy(buf.view(np.float64).copy()), dst=peer)            # the raw buffer only, like ncclSend
+
+        def fake_recv(ctx, legs, dims, peer):
+            n = int(np.prod(dims, dtype=np.int64)) if len(dims) else 1
+            buf = torch.empty(2 * n, dtype=torch.float64)
+            dist.recv(buf, src=peer)
+            t = Tensor(legs, dims)
+            t.set_tensor_data(TensorData.Matrix(buf.numpy().view(np.complex128).reshape(dims)))
+            return t
+
+        class FakePlan:
+            def __init__(self, tn, path, ctx=None):
+                self.tn, self.path = tn, path
+
+            def stage(self, tn):
+                self.tn = tn
+
+            def run(self):
+                return fake_contract(self.tn, self.path)
+
+        con_mod.contract_tensor_network = fake_contract
+        con_mod.NetworkPlan = FakePlan
+        comm_mod._send, comm_mod._recv = fake_send, fake_recv
+        tn, fpath, ptn, ppath = build_case(12, 6, 7, world) if rank == 0 else (None, None, None, None)
+        res = comm_mod.contract_partitioned(ptn, ppath, None)
+        plan = comm_mod.PartitionedPlan(ptn, ppath, None)
+        res2, res3 = plan.run(), plan.run()
+        if rank == 0:
+            flat = complex(orc.contract_tensor_network(to_o(tn), to_op(fpath)).data)
+            one = complex(orc.contract_tensor_network(to_o(ptn), to_op(ppath)).data)      # the nested path on one process
+            for r in (res, res2, res3):
+                assert r.legs == []
+                amp = complex(np.asarray(r.tensordata.matrix))
+                assert abs(amp - flat) <= 1e-10 * abs(flat) + 1e-14 and abs(amp - one) <= 1e-12 * abs(one) + 1e-14, (amp, flat, one)
+            q.put((rank, ("ok", len(plan.events))))
+        else:
+            q.put((rank, ("ok", len(plan.events))))
+    finally:
+        dist.destroy_process_group()
+
+
 def gpu_main():
     """torchrun entry on the GPU box: partitioned contraction over NCCL == flat contraction."""
     import time

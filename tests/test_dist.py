@@ -36,6 +36,24 @@ def test_gloo_host_logic(built_lib, world):
     assert sorted(r for _, r in res[0][0]) == list(range(world))
 
 
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_gloo_full_fanin_with_the_oracle_as_engine(built_lib, world):
+    """contract_partitioned and PartitionedPlan end to end on CPU ranks: the amplitude after scatter + local contraction +
+    fan-in equals the flat one (see dist_worker.cpu_fanin)."""
+    import dist_worker
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = free_port()
+    procs = [ctx.Process(target=dist_worker.cpu_fanin, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    res = dict(q.get(timeout=5) for _ in range(world))
+    assert all(res[r] == ("ok", world - 1) for r in range(world))
+
+
 def test_partition_packing_round_trips(built_lib):
     """the compact form partitions travel in (dist.communication._pack_tensor) loses nothing: nested composites, gate,
     matrix, file and empty leaves"""
