@@ -76,3 +76,46 @@ def test_committed_bench_plan_matches_the_network():
         assert len(ptn.tensors) == n and sorted(path.nested) == list(range(n)) and len(path.toplevel) == n - 1
         assert sum(len(c.tensors) for c in ptn.tensors) == len(tn.tensors) == 489 and validate_path(path)
         assert facts["partition_sizes"] == [len(c.tensors) for c in ptn.tensors]
+
+
+@pytest.mark.parametrize("name", ["sycamore53_d12.json", "sycamore53_d12_alt.json"])
+def test_committed_config5_paths_match_the_network(name):
+    """bench.py's config5 object replays bench_inputs/sycamore53_d12.json on sycamore_circuit(53, 12), seed 1: the committed
+    replace-left path must be valid for exactly that network (1053 tensors, every slot consumed once, scalar at the end), its
+    sliced legs must be summed legs, and the recorded flop count / peak size must be what the path gives."""
+    import json
+    from tnc_b200.builders import sycamore_circuit
+    from tnc_b200.contractionpath import ContractionPath
+    from tnc_b200.contractionpath.slicing import path_cost
+    p = os.path.join(ROOT, "bench_inputs", name)
+    if not os.path.exists(p):
+        pytest.skip(name + " not committed")
+    d = json.load(open(p))
+    w = d["network"].split()
+    assert (w[0], w[1], w[3], w[5]) == ("sycamore", "53q", "12", "1")
+    tn = sycamore_circuit(53, 12, np.random.default_rng(1)).into_amplitude_network("0" * 53)[0]
+    assert len(tn.tensors) == 1053
+    path = ContractionPath.simple([tuple(x) for x in d["toplevel"]])
+    assert len(path.toplevel) == 1052 and validate_path(path)
+    alive = [True] * 1053
+    for i, j in path.toplevel:
+        assert alive[i] and alive[j] and i != j
+        alive[j] = False
+    assert sum(alive) == 1
+    meta = [(t.legs, t.bond_dims) for t in tn.tensors]
+    count = {}
+    for legs, _ in meta:
+        for l in legs:
+            count[l] = count.get(l, 0) + 1
+    assert all(count.get(l) == 2 for l in d["sliced_legs"]), "sliced legs must be bonds between two tensors"
+    assert 2 ** len(d["sliced_legs"]) == d["n_slices"]
+    flops, peak, peak_legs = path_cost(meta, path, d["sliced_legs"])
+    assert peak <= 2.0 ** 30 and peak == d["peak_elements"]
+    assert abs(flops / 8.0 - d["flops_mnk_per_slice"]) <= 1e-9 * d["flops_mnk_per_slice"]
+    # the whole network contracts to a scalar along the path
+    ts = [dict(zip(l, dd)) for l, dd in meta]
+    for i, j in path.toplevel:
+        a, b = ts[i], ts[j]
+        ts[i] = {**{l: x for l, x in b.items() if l not in a}, **{l: x for l, x in a.items() if l not in b}}
+        ts[j] = None
+    assert [t for t in ts if t is not None] == [{}]
