@@ -256,6 +256,13 @@ typedef struct tncb_path {
 int tncb_contract_tensor_network(tncb_ctx* ctx, const tncb_tn* tn, const tncb_path* path,
                                  tncb_tensor** out, int* n_out, uint64_t* out_legs);
 
+/* Legs and bond dimensions of the result of tncb_contract_tensor_network(tn, path), from metadata alone (host only, no
+ * GPU work; the same validation and the same errors as the real call).  The fan-in needs it: only the raw buffer of a
+ * contracted partition travels (tncb_comm_send), so the receiver derives the leg order of what arrives from the sender's
+ * partition and local path (the reference ships legs inside the serialised tensor, serialization.rs:43-67).
+ * out_legs / out_dims need room for 64 entries; either may be NULL. */
+int tncb_network_out_legs(const tncb_tn* tn, const tncb_path* path, int* n_out, uint64_t* out_legs, uint64_t* out_dims);
+
 /* Compile once / execute many: the same circuit with different payloads
  * (e.g. other bitstrings or angles) re-uses the schedule, arena layout and the
  * captured CUDA graph. */

@@ -228,3 +228,42 @@ def test_marshalled_tree_round_trips(built_lib):
                 host_ptrs[id(t.tensordata.matrix)] = np.asarray(t.tensordata.matrix).__array_interface__["data"][0]
         walk(tn)
         assert got == expect(tn, host_ptrs)
+
+
+def test_network_out_legs_matches_the_python_replay(built_lib):
+    """tncb_network_out_legs (metadata only, no GPU) == dist.communication.contracted_legs == the oracle's result legs, for
+    flat and nested paths; errors are the real call's"""
+    from tnc_b200 import TncbError
+    from tnc_b200._lib import check, u64_array
+    from tnc_b200.builders import random_circuit_builder
+    from tnc_b200.contractionpath import ContractionPath
+    from tnc_b200.contractionpath.paths import Cotengrust
+    from tnc_b200.dist.communication import contracted_legs
+    from tnc_b200.tensornetwork import Tensor
+    from tnc_b200.tensornetwork import contraction as ct
+
+    def native(tn, path):
+        m = ct._Marshal()
+        c_tn, c_path = m.tn(tn), m.path(path)
+        n = C.c_int()
+        legs, dims = u64_array([0] * 64), u64_array([0] * 64)
+        check(built_lib.tncb_network_out_legs(C.byref(c_tn), C.byref(c_path), C.byref(n), legs, dims))
+        return [int(legs[i]) for i in range(n.value)], [int(dims[i]) for i in range(n.value)]
+
+    def greedy(tn):
+        o = Cotengrust(tn); o.find_path()
+        return o.get_best_replace_path()
+
+    sv, _ = random_circuit_builder(8, 5, 0.6, 0.6, np.random.default_rng(4)).into_statevector_network()     # 8 open legs
+    p = greedy(sv)
+    assert native(sv, p) == contracted_legs(sv, p) and len(native(sv, p)[0]) == 8
+    n = len(sv.tensors)
+    nested = Tensor.new_composite([Tensor.new_composite(sv.tensors[:n // 2]), Tensor.new_composite(sv.tensors[n // 2:])])
+    pn = greedy(nested)
+    assert sorted(pn.nested) == [0, 1]
+    assert native(nested, pn) == contracted_legs(nested, pn)
+    for i in (0, 1):      # a partition on its own: what the receiver of the fan-in is told
+        assert native(nested.tensor(i), pn.nested[i]) == contracted_legs(nested.tensor(i), pn.nested[i])
+    with pytest.raises(TncbError) as e:          # not fully contracted (contraction.rs:50)
+        native(sv, ContractionPath.simple(p.toplevel[:-1]))
+    assert e.value.status == -4

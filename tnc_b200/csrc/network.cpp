@@ -776,6 +776,24 @@ int tncb_plan_run_slices(tncb_ctx* ctx, tncb_plan* plan, size_t first, size_t st
   return TNCB_OK;
 }
 
+// Legs and bond dimensions of contract_tensor_network(tn, path) from metadata alone (no GPU work): what a receiver of the
+// fan-in needs to know about a raw buffer it is about to get (communication.rs:221-226; the reference ships the legs inside
+// the serialised tensor instead).
+int tncb_network_out_legs(const tncb_tn* tn, const tncb_path* path, int* n_out, uint64_t* out_legs, uint64_t* out_dims) {
+  if (!tn || !n_out) return tncb::fail(TNCB_ERR_INVALID, "null argument");
+  tncb::Schedule S;
+  int rc = tncb::build_schedule(tn, path, S);
+  if (rc) return rc;
+  if (S.result_slot < 0) { *n_out = 0; return TNCB_OK; }
+  const tncb::SlotMeta& m = S.slots[S.result_slot];
+  *n_out = (int)m.legs.size();
+  for (size_t i = 0; i < m.legs.size(); i++) {
+    if (out_legs) out_legs[i] = m.legs[i];
+    if (out_dims) out_dims[i] = m.dims[i];
+  }
+  return TNCB_OK;
+}
+
 int tncb_plan_info(const tncb_plan* plan, uint64_t* n_pairs, double* flops, double* bytes, uint64_t* peak_bytes, uint64_t* n_kernels) {
   if (!plan) return tncb::fail(TNCB_ERR_INVALID, "plan is null");
   const tncb::Schedule& S = plan->S;
