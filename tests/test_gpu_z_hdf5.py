@@ -58,12 +58,15 @@ def test_file_leaves_equal_matrix_leaves(ctx, tmp_path):
     a_file = complex(contract_tensor_network(file_tn, path, ctx=ctx).to_numpy())
     a_file2 = complex(contract_tensor_network(file_tn, path, ctx=ctx).to_numpy())      # second call: cached plan, files re-read
     assert a_mat == a_gate and a_file == a_mat and a_file2 == a_mat
-    # against the oracle on the in-memory variant
+    # against the oracle, which reads the same files with a reader of its own (oracle.load_data_hdf5) and adjoints them itself
     def to_o(t):
         if t.is_composite():
             return orc.OTensor(children=[to_o(c) for c in t.tensors])
-        return orc.OTensor(list(t.legs), list(t.bond_dims), np.asarray(t.tensordata.matrix))
-    ref = complex(orc.contract_tensor_network(to_o(mat_tn), orc.OPath(list(path.toplevel), {})).data)
+        td = t.tensordata
+        return orc.OTensor(list(t.legs), list(t.bond_dims), ("file", td.file[0], td.file[1]) if td.kind == "file" else np.asarray(td.matrix))
+    ref = complex(orc.contract_tensor_network(to_o(file_tn), orc.OPath(list(path.toplevel), {})).data)
+    ref_mat = complex(orc.contract_tensor_network(to_o(mat_tn), orc.OPath(list(path.toplevel), {})).data)
+    assert ref == ref_mat
     assert abs(a_file - ref) <= 1e-9 * abs(ref) + 1e-18
 
 

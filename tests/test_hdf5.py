@@ -286,6 +286,26 @@ def test_file_leaf_into_data(h5, built_lib, tmp_path):
     np.testing.assert_array_equal(_load_leaf(built_lib, tmp_path / "m.h5", True, [8, 2]).shape, (8, 2))
 
 
+def test_oracle_reader_agrees(h5, tmp_path):
+    """the oracle's own File-leaf reader (oracle.load_data_hdf5, shares no code with csrc/hdf5io.cpp) returns what the
+    library returns, also behind a three-level group B-tree, and the oracle's File payload applies the adjoint rule"""
+    from oracle import tnc_oracle as orc
+    rng = np.random.default_rng(8)
+    a = cplx(rng, (2, 3, 2, 3))
+    h5.store_data(tmp_path / "a.h5", a)
+    np.testing.assert_array_equal(orc.load_data_hdf5(tmp_path / "a.h5"), a)
+    np.testing.assert_array_equal(orc.load_data_hdf5(tmp_path / "a.h5"), h5.load_data(tmp_path / "a.h5"))
+    t = orc.OTensor([0, 1, 2, 3], [2, 3, 2, 3], ("file", str(tmp_path / "a.h5"), True))
+    np.testing.assert_array_equal(t.materialise(), np.conj(np.transpose(a, [2, 3, 0, 1])))
+    many = [(str(i), [i], cplx(rng, (2,))) for i in range(2100)]
+    h5.store_tensor(tmp_path / "many.h5", many, [0])
+    assert orc.load_data_hdf5(tmp_path / "many.h5").shape == ()              # "-1" sorts first: declared, never written
+    h5.store_tensor(tmp_path / "many.h5", many[5:], [0])                      # now "-1" ... still first
+    with h5.Hdf5File(tmp_path / "many.h5") as f:
+        first_with_data = f.member_names()[1]
+    assert first_with_data == "10"
+
+
 def test_file_tensordata_mirror(h5):
     from tnc_b200.tensornetwork.tensordata import TensorData
     td = TensorData.File("x.h5", False)
