@@ -468,7 +468,8 @@ def run_ours(args):
 
     # ---- e2e: the public call from host leaves, device->host read of the amplitude inside -----------------
     e2e_steps = max(3, min(args.steps, 10))
-    read_amp(step_e2e())
+    for _ in range(warmup):       # W >= 3 like the resident form: the library compiles its plan on the SECOND sighting of a structure
+        read_amp(step_e2e())
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     w0 = time.perf_counter()
