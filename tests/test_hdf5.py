@@ -364,3 +364,39 @@ def test_corrupted_files_are_rejected_not_followed(h5, tmp_path, kind):
     assert r.returncode == 0, r.stderr[-2000:]
     ok, bad = map(int, r.stdout.split())
     assert ok + bad == 600 and bad > 50
+
+
+def test_network_file_round_trip_contracts_to_the_same_amplitude(h5, tmp_path):
+    """a circuit network written as /tensors/<i>{bids} (gates materialised), read back with load_tensor -- members arrive in
+    name order "0", "1", "10", "11", ..., not in circuit order -- and contracted by the oracle along a path found on the
+    LOADED network gives the amplitude of the original network"""
+    from oracle import tnc_oracle as orc
+    from tnc_b200.builders import random_circuit
+    from tnc_b200.contractionpath.paths import Cotengrust
+    from tnc_b200.gates import load_gate, load_gate_adjoint
+    tn = random_circuit(10, 6, 0.6, 0.6, np.random.default_rng(12))
+
+    def payload(t):
+        td = t.tensordata
+        if td.kind == "gate":
+            return (load_gate_adjoint if td.gate[2] else load_gate)(td.gate[0], td.gate[1]).reshape(t.bond_dims)
+        return np.asarray(td.matrix, dtype=np.complex128).reshape(t.bond_dims)
+
+    h5.store_tensor(tmp_path / "net.h5", [(str(i), t.legs, payload(t)) for i, t in enumerate(tn.tensors)], [])
+    loaded = h5.load_tensor(tmp_path / "net.h5")
+    assert loaded.legs == [] and len(loaded.tensors) == len(tn.tensors)
+    order = sorted(range(len(tn.tensors)), key=lambda i: str(i).encode())
+    assert [t.legs for t in loaded.tensors] == [tn.tensors[i].legs for i in order]
+
+    def amplitude(net):
+        opt = Cotengrust(net); opt.find_path()
+        path = opt.get_best_replace_path()
+        def to_o(t):
+            if t.is_composite():
+                return orc.OTensor(children=[to_o(c) for c in t.tensors])
+            td = t.tensordata
+            return orc.OTensor(list(t.legs), list(t.bond_dims), ("gate", td.gate[0], td.gate[1], td.gate[2]) if td.kind == "gate" else np.asarray(td.matrix))
+        return complex(orc.contract_tensor_network(to_o(net), orc.OPath(list(path.toplevel), {})).data)
+
+    a, b = amplitude(tn), amplitude(loaded)
+    assert abs(a - b) <= 1e-13 * abs(a)
