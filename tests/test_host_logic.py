@@ -267,3 +267,25 @@ def test_network_out_legs_matches_the_python_replay(built_lib):
     with pytest.raises(TncbError) as e:          # not fully contracted (contraction.rs:50)
         native(sv, ContractionPath.simple(p.toplevel[:-1]))
     assert e.value.status == -4
+
+
+def test_null_arguments_never_crash(built_lib):
+    """every exported entry point called with zero / NULL for every argument returns (a status, 0 or NULL) instead of
+    dereferencing: the Rust shim turns statuses into panics, a segfault would take the host down.  One child process, so
+    that a crash is seen as one (the name of the call in flight is the last line it printed)."""
+    import subprocess
+    import sys
+    code = r"""
+import sys, ctypes as C
+sys.path.insert(0, %r)
+from tnc_b200._lib import SIGNATURES, lib
+l = lib()
+for name in sorted(SIGNATURES):
+    res, args = SIGNATURES[name]
+    vals = [0 if a in (C.c_int, C.c_size_t, C.c_longlong, C.c_uint64, C.c_int64) else 0.0 if a is C.c_double else None for a in args]
+    print(name, flush=True)
+    getattr(l, name)(*vals)
+print("SWEEP_OK", len(SIGNATURES))
+""" % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "SWEEP_OK" in r.stdout, (r.returncode, r.stdout.strip().splitlines()[-1:], r.stderr[-500:])
