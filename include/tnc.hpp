@@ -223,6 +223,133 @@ class NetworkPlan {
   tncb_plan* h_ = nullptr;
 };
 
+// tnc::builders (tnc/src/builders/circuit_builder.rs): Permutor (:72-129) and Circuit (:135-335).
+namespace builders {
+
+// TensorData::adjoint (tensordata.rs:62-72) for the payload kinds a circuit holds
+inline TensorData adjoint(const TensorData& d, const std::vector<uint64_t>& dims) {
+  TensorData a = d;
+  if (d.kind == TensorData::Gate || d.kind == TensorData::File) { a.adjoint = !d.adjoint; return a; }
+  if (d.kind != TensorData::Matrix) return a;
+  const size_t r = dims.size(), half = r / 2;
+  size_t rows = 1, cols = 1;
+  for (size_t i = 0; i < half; i++) rows *= dims[i];
+  for (size_t i = half; i < r; i++) cols *= dims[i];
+  for (size_t i = 0; i < rows; i++)
+    for (size_t j = 0; j < cols; j++) a.matrix[j * rows + i] = std::conj(d.matrix[i * cols + j]);
+  return a;
+}
+
+class Permutor {
+ public:
+  explicit Permutor(std::vector<uint64_t> target) : target_leg_order(std::move(target)) {}
+  bool is_identity() const { return target_leg_order.empty(); }
+  // permutation p with given[p[i]] == target[i] (circuit_builder.rs:125-129)
+  static std::vector<int> permutation_between(const std::vector<uint64_t>& given, const std::vector<uint64_t>& target) {
+    if (given.size() != target.size()) throw Error(TNCB_ERR_INVALID, "given and target must be permutations of each other");
+    std::vector<int> p;
+    for (uint64_t l : target) {
+      size_t q = 0;
+      while (q < given.size() && given[q] != l) q++;
+      if (q == given.size()) throw Error(TNCB_ERR_INVALID, "given and target must be permutations of each other");
+      p.push_back((int)q);
+    }
+    return p;
+  }
+  // Permutor::apply (:86-114): transposes the device data into the target leg order (one tncb_permute launch)
+  Tensor apply(Context& ctx, Tensor t) const {
+    if (is_identity()) return t;
+    if (t.tensordata.kind != TensorData::Device) throw Error(TNCB_ERR_UNCONTRACTED, "Permutor::apply needs a contracted (device) tensor");
+    std::vector<int> perm = permutation_between(t.legs, target_leg_order);
+    tncb_tensor* out = nullptr;
+    check(tncb_permute(ctx.get(), t.tensordata.device->t, perm.data(), &out));
+    t.tensordata.device->t = nullptr;                 // consumed
+    Tensor res(target_leg_order, {});
+    for (int q : perm) res.bond_dims.push_back(t.bond_dims[q]);
+    res.tensordata.kind = TensorData::Device;
+    res.tensordata.device = std::make_shared<DeviceData>();
+    res.tensordata.device->ctx = ctx.get(); res.tensordata.device->t = out;
+    return res;
+  }
+  std::vector<uint64_t> target_leg_order;
+};
+
+class Circuit {
+ public:
+  size_t num_qubits() const { return open_edges_.size(); }
+  // allocate_register (:184-203): returns the indices of the new qubits
+  std::vector<size_t> allocate_register(size_t size) {
+    std::vector<size_t> reg;
+    for (size_t i = 0; i < size; i++) {
+      reg.push_back(num_qubits());
+      const uint64_t e = next_edge_++;
+      open_edges_.push_back(e);
+      Tensor ket = Tensor::new_from_const({e}, 2);
+      ket.set_tensor_data(ket_data(0));
+      tensors_.push_back(std::move(ket));
+    }
+    return reg;
+  }
+  // append_gate (:205-241): legs = [old edges ..., new edges ...]
+  void append_gate(TensorData gate, const std::vector<size_t>& qubits) {
+    for (size_t i = 0; i < qubits.size(); i++)
+      for (size_t j = i + 1; j < qubits.size(); j++)
+        if (qubits[i] == qubits[j]) throw Error(TNCB_ERR_INVALID, "Qubit arguments must be unique");
+    std::vector<uint64_t> edges;
+    for (size_t q : qubits) edges.push_back(open_edges_.at(q));
+    for (size_t i = 0; i < qubits.size(); i++) { edges.push_back(next_edge_ + i); open_edges_[qubits[i]] = next_edge_ + i; }
+    next_edge_ += qubits.size();
+    Tensor t = Tensor::new_from_const(std::move(edges), 2);
+    t.set_tensor_data(std::move(gate));
+    tensors_.push_back(std::move(t));
+  }
+  // into_amplitude_network (:243-277): '0' / '1' close a qubit with a bra, '*' leaves it open
+  std::pair<Tensor, Permutor> into_amplitude_network(const std::string& bitstring) && {
+    if (bitstring.size() != num_qubits()) throw Error(TNCB_ERR_INVALID, "bitstring length differs from the number of qubits");
+    std::vector<uint64_t> final_legs;
+    for (size_t q = 0; q < bitstring.size(); q++) {
+      const char c = bitstring[q];
+      if (c == '*') { final_legs.push_back(open_edges_[q]); continue; }
+      if (c != '0' && c != '1') throw Error(TNCB_ERR_INVALID, "Only 0, 1 and * are allowed in bitstring");
+      Tensor bra = Tensor::new_from_const({open_edges_[q]}, 2);
+      bra.set_tensor_data(ket_data(c - '0'));
+      tensors_.push_back(std::move(bra));
+    }
+    return {Tensor::new_composite(std::move(tensors_)), Permutor(std::move(final_legs))};
+  }
+  std::pair<Tensor, Permutor> into_statevector_network() && { return std::move(*this).into_amplitude_network(std::string(num_qubits(), '*')); }
+  // into_expectation_value_network (:315-335): the circuit, its adjoint mirror image (legs + offset) and a layer of Z
+  Tensor into_expectation_value_network() && {
+    const uint64_t offset = next_edge_;
+    const size_t n = tensors_.size();
+    for (size_t i = 0; i < n; i++) {
+      const Tensor& t = tensors_[i];
+      const size_t half = t.legs.size() / 2;
+      Tensor a;
+      for (size_t q = half; q < t.legs.size(); q++) { a.legs.push_back(t.legs[q] + offset); a.bond_dims.push_back(t.bond_dims[q]); }
+      for (size_t q = 0; q < half; q++) { a.legs.push_back(t.legs[q] + offset); a.bond_dims.push_back(t.bond_dims[q]); }
+      a.set_tensor_data(adjoint(t.tensordata, t.bond_dims));
+      tensors_.push_back(std::move(a));
+    }
+    for (uint64_t e : open_edges_) {
+      Tensor z = Tensor::new_from_const({e, e + offset}, 2);
+      z.set_tensor_data(TensorData::gate("z"));
+      tensors_.push_back(std::move(z));
+    }
+    return Tensor::new_composite(std::move(tensors_));
+  }
+
+ private:
+  static TensorData ket_data(int bit) {
+    return TensorData::new_from_data({2}, bit == 0 ? std::vector<Complex64>{{1, 0}, {0, 0}} : std::vector<Complex64>{{0, 0}, {1, 0}});
+  }
+  std::vector<uint64_t> open_edges_;
+  uint64_t next_edge_ = 0;
+  std::vector<Tensor> tensors_;
+};
+
+}  // namespace builders
+
 // tnc::io::hdf5 (tnc/src/io/hdf5.rs): /tensors/<name> datasets with `bids` attributes, "-1" = the output tensor.
 namespace io { namespace hdf5 {
 namespace detail {

@@ -119,6 +119,52 @@ static void test_hdf5_write_read(const std::string& dir) {
   EXPECT(threw);
 }
 
+// builders::Circuit / Permutor: structure only (no GPU).  Leg numbering as circuit_builder.rs:184-277 produces it; the same
+// circuit as test_bell_contract below builds by hand.
+static void test_circuit_builder_structure() {
+  using builders::Circuit; using builders::Permutor;
+  Circuit c;
+  auto q = c.allocate_register(2);
+  c.append_gate(TensorData::gate("h"), {q[0]});
+  c.append_gate(TensorData::gate("cx"), {q[0], q[1]});
+  EXPECT(c.num_qubits() == 2);
+  Circuit c2 = c;
+  auto sv = std::move(c).into_statevector_network();
+  const std::vector<std::vector<uint64_t>> legs = {{0}, {1}, {0, 2}, {2, 1, 3, 4}};
+  EXPECT(sv.first.tensors.size() == 4);
+  for (size_t i = 0; i < 4 && i < sv.first.tensors.size(); i++) {
+    EXPECT(sv.first.tensor(i).legs == legs[i]);
+    EXPECT(sv.first.tensor(i).bond_dims == std::vector<uint64_t>(legs[i].size(), 2));
+  }
+  EXPECT((sv.second.target_leg_order == std::vector<uint64_t>{3, 4}));
+  EXPECT(sv.first.tensor(2).tensordata.kind == TensorData::Gate && sv.first.tensor(2).tensordata.gate_name == "h");
+  auto amp = std::move(c2).into_amplitude_network("1*");
+  EXPECT(amp.first.tensors.size() == 5 && (amp.first.tensor(4).legs == std::vector<uint64_t>{3}));
+  EXPECT((amp.first.tensor(4).tensordata.matrix == std::vector<Complex64>{{0, 0}, {1, 0}}));
+  EXPECT((amp.second.target_leg_order == std::vector<uint64_t>{4}));
+  // expectation value network: 4 tensors, their adjoints on legs + 5, one Z per qubit
+  Circuit c3; auto r = c3.allocate_register(2);
+  c3.append_gate(TensorData::gate("h"), {r[0]}); c3.append_gate(TensorData::gate("cx"), {r[0], r[1]});
+  Tensor ev = std::move(c3).into_expectation_value_network();
+  EXPECT(ev.tensors.size() == 10);
+  EXPECT((ev.tensor(7).legs == std::vector<uint64_t>{8, 9, 7, 6}) && ev.tensor(7).tensordata.adjoint);     // cx: halves swapped, + offset 5
+  EXPECT((ev.tensor(8).legs == std::vector<uint64_t>{3, 8}) && ev.tensor(8).tensordata.gate_name == "z");
+  EXPECT((ev.tensor(9).legs == std::vector<uint64_t>{4, 9}));
+  // permutation_between (circuit_builder.rs:357-369)
+  const std::vector<std::pair<std::vector<uint64_t>, std::vector<uint64_t>>> cases = {
+      {{1, 2, 3, 4}, {1, 2, 3, 4}}, {{1, 2, 3, 4}, {4, 3, 2, 1}}, {{4, 3, 2, 1}, {1, 2, 3, 4}}, {{4, 1, 3, 2}, {2, 4, 3, 1}},
+      {{5, 1, 4, 3, 2, 6}, {1, 6, 3, 5, 2, 4}}};
+  for (auto& gt : cases) {
+    auto p = Permutor::permutation_between(gt.first, gt.second);
+    std::vector<uint64_t> applied;
+    for (int i : p) applied.push_back(gt.first[i]);
+    EXPECT(applied == gt.second);
+  }
+  bool threw = false;
+  try { Circuit bad; auto b = bad.allocate_register(2); bad.append_gate(TensorData::gate("cx"), {b[0], b[0]}); } catch (const Error&) { threw = true; }
+  EXPECT(threw);                                                  // "Qubit arguments must be unique"
+}
+
 // TensorData::File leaves (tensordata.rs:43-49) inside contract_tensor_network
 static void test_file_leaf(Context& ctx, const std::string& dir) {
   const std::vector<Complex64> a = {{1, 0}, {2, 5}, {3, -1}}, b = {{-4, 2}, {0, -1}};
@@ -135,7 +181,7 @@ static void test_file_leaf(Context& ctx, const std::string& dir) {
 int main(int argc, char** argv) {
   const std::string dir = argc > 2 ? argv[2] : "/tmp";
   if (argc > 1 && std::strcmp(argv[1], "--io") == 0) {
-    try { test_hdf5_write_read(dir); } catch (const Error& e) { std::printf("FAIL uncaught tnc::Error %d: %s\n", e.status, e.what()); return 2; }
+    try { test_hdf5_write_read(dir); test_circuit_builder_structure(); } catch (const Error& e) { std::printf("FAIL uncaught tnc::Error %d: %s\n", e.status, e.what()); return 2; }
     if (failures) { std::printf("%d failure(s)\n", failures); return 1; }
     std::printf("HOST_IO_OK\n");
     return 0;
